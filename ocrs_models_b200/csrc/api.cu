@@ -1,0 +1,25 @@
+// Library-wide C-ABI plumbing: error string, version, device query.
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void ocrs_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+const char* ocrs_last_error(void) { return g_err; }
+int ocrs_version(void) { return 100; }
+// Compute capability major*10+minor of the current device (100 on B200), or <0 on error.
+int ocrs_device_arch(void) {
+  int dev = 0, maj = 0, min = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return -1;
+  return maj * 10 + min;
+}
+}

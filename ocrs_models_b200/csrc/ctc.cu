@@ -1,0 +1,314 @@
+// CTC loss forward (alpha lattice) and backward (beta lattice + softmax-folded gradient).
+//
+// Replaces torch.nn.CTCLoss() as called at reference ocrs_models/train_rec.py:104,121
+// (blank = 0, reduction = "mean", zero_infinity = False; arithmetic = aten ctc_loss).
+//
+// One warp per sample. The 2S+1 lattice states live in registers, K consecutive states per
+// lane, so the s-1 / s-2 neighbours of a step need two warp shuffles; the three-way
+// log-sum-exp per state is evaluated in fp32 exactly as aten does (max-shifted exp/log).
+// log-prob rows for step t+1 are gathered while step t is being reduced.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int CTC_WARPS = 4;
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+template <int K>
+__global__ void __launch_bounds__(CTC_WARPS * 32)
+ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, int tgt_stride,
+                 const int* __restrict__ in_len, const int* __restrict__ tgt_len,
+                 float* __restrict__ alpha, float* __restrict__ nll, int T, int N, int C,
+                 int blank) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * CTC_WARPS + (threadIdx.x >> 5);
+  if (n >= N) return;
+  constexpr int LROW = 32 * K;
+  const int S = max(tgt_len[n], 0);
+  const int L = 2 * S + 1;
+  const int Tn = min(in_len[n], T);
+  const int* tg = targets + (size_t)n * tgt_stride;
+
+  int lab[K];
+  bool skip[K];
+  float a[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = lane * K + k;
+    int l = blank;
+    bool sk = false;
+    if (s < L && (s & 1)) {
+      l = tg[s >> 1];
+      sk = (s >= 3) && (tg[(s >> 1) - 1] != l);
+    }
+    lab[k] = l;
+    skip[k] = sk;
+  }
+  float* arow = alpha + (size_t)n * T * LROW + lane * K;
+  if (Tn <= 0) {
+    if (lane == 0) nll[n] = (S == 0) ? 0.f : INFINITY;
+    return;
+  }
+  const float* row = lp + (size_t)n * C;
+  const size_t tstride = (size_t)N * C;
+  float cur[K], nxt[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) cur[k] = (lane * K + k < L) ? row[lab[k]] : 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = lane * K + k;
+    a[k] = (s < 2 && s < L) ? cur[k] : -INFINITY;
+    arow[k] = a[k];
+  }
+  for (int t = 1; t < Tn; ++t) {
+    row += tstride;
+#pragma unroll
+    for (int k = 0; k < K; ++k) nxt[k] = (lane * K + k < L) ? row[lab[k]] : 0.f;
+    // neighbours owned by the previous lane
+    float p1 = __shfl_up_sync(0xffffffffu, a[K - 1], 1);
+    float p2 = __shfl_up_sync(0xffffffffu, K >= 2 ? a[K >= 2 ? K - 2 : 0] : -INFINITY, 1);
+    if (K == 1) {
+      // with one state per lane s-2 lives two lanes back
+      p2 = __shfl_up_sync(0xffffffffu, a[0], 2);
+      if (lane < 2) p2 = -INFINITY;
+    }
+    if (lane == 0) { p1 = -INFINITY; p2 = -INFINITY; }
+    float an[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float m1 = (k >= 1) ? a[k >= 1 ? k - 1 : 0] : p1;
+      const float m2 = (k >= 2) ? a[k >= 2 ? k - 2 : 0] : ((k == 1) ? p1 : p2);
+      // (k == 1) uses previous lane's last state as s-2, (k == 0) its second-to-last
+      const float s2 = skip[k] ? m2 : -INFINITY;
+      an[k] = (lane * K + k < L) ? lse3(a[k], m1, s2) + nxt[k] : -INFINITY;
+    }
+    arow += LROW;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a[k] = an[k]; arow[k] = an[k]; }
+  }
+  // nll = -logsumexp(alpha[Tn-1][L-1], alpha[Tn-1][L-2])
+  float last = -INFINITY, last2 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = lane * K + k;
+    if (s == L - 1) last = a[k];
+    if (s == L - 2) last2 = a[k];
+  }
+  last = warp_max(last);
+  last2 = warp_max(last2);
+  if (lane == 0) {
+    float m = fmaxf(last, last2);
+    float r = (m == -INFINITY) ? -INFINITY : m + logf(expf(last - m) + expf(last2 - m));
+    nll[n] = -r;
+  }
+}
+
+// mode: 0 = none (gout[n]), 1 = mean (gout[0] / (N * max(S,1))), 2 = sum (gout[0])
+template <int K>
+__global__ void __launch_bounds__(CTC_WARPS * 32)
+ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targets,
+                     int tgt_stride, const int* __restrict__ in_len,
+                     const int* __restrict__ tgt_len, const float* __restrict__ alpha,
+                     const float* __restrict__ nll, const float* __restrict__ gout, int mode,
+                     int zero_infinity, float* __restrict__ grad, int T, int N, int C,
+                     int blank) {
+  extern __shared__ float occ_all[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int n = blockIdx.x * CTC_WARPS + wid;
+  if (n >= N) return;
+  float* occ = occ_all + wid * C;
+  constexpr int LROW = 32 * K;
+  const int S = max(tgt_len[n], 0);
+  const int L = 2 * S + 1;
+  const int Tn = min(in_len[n], T);
+  const int* tg = targets + (size_t)n * tgt_stride;
+  const size_t tstride = (size_t)N * C;
+
+  float gs = (mode == 0) ? gout[n] : gout[0];
+  if (mode == 1) gs /= ((float)N * (float)max(S, 1));
+  const float nl = nll[n];
+  const bool dead = zero_infinity && (nl == INFINITY);
+
+  // frames at or beyond the sample's input length get zero gradient
+  for (int t = max(Tn, 0); t < T; ++t) {
+    float* g = grad + (size_t)t * tstride + (size_t)n * C;
+    for (int c = lane; c < C; c += 32) g[c] = 0.f;
+  }
+  if (Tn <= 0) return;
+  if (dead) {
+    for (int t = 0; t < Tn; ++t) {
+      float* g = grad + (size_t)t * tstride + (size_t)n * C;
+      for (int c = lane; c < C; c += 32) g[c] = 0.f;
+    }
+    return;
+  }
+
+  int lab[K];
+  bool skip[K];  // transition s -> s+2 allowed
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = lane * K + k;
+    int l = blank;
+    bool sk = false;
+    if (s < L && (s & 1)) {
+      l = tg[s >> 1];
+      sk = (s + 2 < L) && (tg[(s >> 1) + 1] != l);
+    }
+    lab[k] = l;
+    skip[k] = sk;
+  }
+
+  float b[K];
+  const float* arow = alpha + ((size_t)n * T + (Tn - 1)) * LROW + lane * K;
+  const float* row = lp + (size_t)(Tn - 1) * tstride + (size_t)n * C;
+  float cur[K], av[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = lane * K + k;
+    cur[k] = (s < L) ? row[lab[k]] : 0.f;
+    av[k] = arow[k];
+    b[k] = (s < L && s >= L - 2) ? cur[k] : -INFINITY;
+  }
+  for (int t = Tn - 1; t >= 0; --t) {
+    // prefetch t-1
+    float nxt[K], an[K];
+    const float* prow = row - tstride;
+    const float* parow = arow - LROW;
+    if (t > 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        nxt[k] = (lane * K + k < L) ? prow[lab[k]] : 0.f;
+        an[k] = parow[k];
+      }
+    }
+    // this frame's gradient row from alpha(t) + beta(t)
+    for (int c = lane; c < C; c += 32) occ[c] = 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (lane * K + k < L) {
+        const float v = av[k] + b[k] + nl - cur[k];
+        if (v > -INFINITY) atomicAdd(&occ[lab[k]], expf(v));
+      }
+    }
+    __syncwarp();
+    float* g = grad + (size_t)t * tstride + (size_t)n * C;
+    for (int c = lane; c < C; c += 32) g[c] = (expf(row[c]) - occ[c]) * gs;
+    __syncwarp();
+    if (t == 0) break;
+    // beta(t-1)[s] = lse(beta(t)[s], beta(t)[s+1], skip ? beta(t)[s+2]) + lp[t-1][l_s]
+    float n1 = __shfl_down_sync(0xffffffffu, b[0], 1);
+    float n2 = __shfl_down_sync(0xffffffffu, K >= 2 ? b[K >= 2 ? 1 : 0] : -INFINITY, 1);
+    if (K == 1) {
+      n2 = __shfl_down_sync(0xffffffffu, b[0], 2);
+      if (lane >= 30) n2 = -INFINITY;
+    }
+    if (lane == 31) { n1 = -INFINITY; n2 = -INFINITY; }
+    float bn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float u1 = (k + 1 < K) ? b[k + 1 < K ? k + 1 : 0] : n1;
+      const float u2 = (k + 2 < K) ? b[k + 2 < K ? k + 2 : 0] : ((k + 1 < K) ? n1 : n2);
+      // (k == K-2) takes next lane's first state as s+2, (k == K-1) its second
+      const float s2 = skip[k] ? u2 : -INFINITY;
+      const int s = lane * K + k;
+      bn[k] = (s < L) ? lse3(b[k], (s + 1 < L) ? u1 : -INFINITY, s2) + nxt[k] : -INFINITY;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { b[k] = bn[k]; cur[k] = nxt[k]; av[k] = an[k]; }
+    row = prow;
+    arow = parow;
+  }
+}
+
+// loss = reduce(nll) with aten's conventions (mean: mean_n(nll_n / max(S_n, 1))).
+__global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int* __restrict__ tgt_len,
+                                  float* __restrict__ loss, int N, int mode, int zero_infinity) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float v = nll[n];
+    if (zero_infinity && v == INFINITY) v = 0.f;
+    if (mode == 1) v /= (float)max(tgt_len[n], 1);
+    acc += v;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = (mode == 1) ? acc / (float)N : acc;
+}
+
+int pick_k(int max_S) {
+  const int L = 2 * max_S + 1;
+  const int ks[] = {1, 2, 3, 4, 5, 6, 8, 12, 16};
+  for (int k : ks)
+    if (32 * k >= L) return k;
+  return 0;
+}
+
+}  // namespace
+
+#define CTC_DISPATCH(K_, ...)                \
+  switch (K_) {                              \
+    case 1: { constexpr int K = 1; __VA_ARGS__; break; }   \
+    case 2: { constexpr int K = 2; __VA_ARGS__; break; }   \
+    case 3: { constexpr int K = 3; __VA_ARGS__; break; }   \
+    case 4: { constexpr int K = 4; __VA_ARGS__; break; }   \
+    case 5: { constexpr int K = 5; __VA_ARGS__; break; }   \
+    case 6: { constexpr int K = 6; __VA_ARGS__; break; }   \
+    case 8: { constexpr int K = 8; __VA_ARGS__; break; }   \
+    case 12: { constexpr int K = 12; __VA_ARGS__; break; } \
+    case 16: { constexpr int K = 16; __VA_ARGS__; break; } \
+    default: break;                          \
+  }
+
+extern "C" {
+
+// Row length (floats) of the alpha workspace for targets of at most max_S labels; 0 if unsupported.
+int ocrs_ctc_alpha_row(int max_S) { return 32 * pick_k(max_S); }
+
+int ocrs_ctc_fwd(const float* log_probs, const int* targets, int tgt_stride,
+                 const int* input_lengths, const int* target_lengths, int T, int N, int C,
+                 int max_S, int blank, int reduction, int zero_infinity, float* alpha,
+                 float* nll, float* loss, void* stream) {
+  OCRS_CHECK_ARG(T > 0 && N > 0 && C > 0, "ctc_fwd: bad dims T=%d N=%d C=%d", T, N, C);
+  OCRS_CHECK_ARG(blank >= 0 && blank < C, "ctc_fwd: blank %d out of range", blank);
+  const int K_ = pick_k(max_S);
+  OCRS_CHECK_ARG(K_ > 0, "ctc_fwd: target length %d exceeds supported maximum 255", max_S);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ocrs_cdiv(N, CTC_WARPS);
+  CTC_DISPATCH(K_, (ctc_alpha_kernel<K><<<grid, CTC_WARPS * 32, 0, st>>>(
+                       log_probs, targets, tgt_stride, input_lengths, target_lengths, alpha, nll,
+                       T, N, C, blank)));
+  OCRS_CHECK_LAUNCH("ctc_alpha_kernel");
+  if (loss && reduction != 0) {
+    ctc_reduce_kernel<<<1, 256, 0, st>>>(nll, target_lengths, loss, N, reduction, zero_infinity);
+    OCRS_CHECK_LAUNCH("ctc_reduce_kernel");
+  }
+  return 0;
+}
+
+int ocrs_ctc_bwd(const float* log_probs, const int* targets, int tgt_stride,
+                 const int* input_lengths, const int* target_lengths, int T, int N, int C,
+                 int max_S, int blank, int reduction, int zero_infinity, const float* alpha,
+                 const float* nll, const float* grad_out, float* grad_log_probs, void* stream) {
+  OCRS_CHECK_ARG(T > 0 && N > 0 && C > 0, "ctc_bwd: bad dims T=%d N=%d C=%d", T, N, C);
+  const int K_ = pick_k(max_S);
+  OCRS_CHECK_ARG(K_ > 0, "ctc_bwd: target length %d exceeds supported maximum 255", max_S);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ocrs_cdiv(N, CTC_WARPS);
+  const size_t smem = (size_t)CTC_WARPS * C * sizeof(float);
+  OCRS_CHECK_ARG(smem <= 48 * 1024, "ctc_bwd: class count %d too large", C);
+  CTC_DISPATCH(K_, (ctc_beta_grad_kernel<K><<<grid, CTC_WARPS * 32, smem, st>>>(
+                       log_probs, targets, tgt_stride, input_lengths, target_lengths, alpha, nll,
+                       grad_out, reduction, zero_infinity, grad_log_probs, T, N, C, blank)));
+  OCRS_CHECK_LAUNCH("ctc_beta_grad_kernel");
+  return 0;
+}
+
+}  // extern "C"

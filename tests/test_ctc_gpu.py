@@ -1,0 +1,108 @@
+"""CTC kernels (csrc/ctc.cu) through the C-ABI vs the oracle (aten CPU ctc_loss + numpy restatement)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import functional as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_ours(lp, tgt, il, tl, reduction="mean", zero_infinity=False):
+    from ocrs_models_b200 import CTCLoss
+
+    lpd = lp.detach().cuda().requires_grad_(True)
+    loss = CTCLoss(reduction=reduction, zero_infinity=zero_infinity)(lpd, tgt.cuda(), il, tl)
+    loss.sum().backward()
+    return loss.detach().cpu(), lpd.grad.cpu()
+
+
+def _run_oracle(lp, tgt, il, tl, reduction="mean", zero_infinity=False):
+    lpc = lp.detach().clone().requires_grad_(True)
+    loss = O.ctc_loss(lpc, tgt, il, tl, 0, reduction, zero_infinity)
+    loss.sum().backward()
+    return loss.detach(), lpc.grad
+
+
+def test_golden_small(golden):
+    gold = golden("ctc_small")
+    lp = torch.from_numpy(gold["lp"])
+    tgt, il, tl = (torch.from_numpy(gold[k]) for k in ("targets", "il", "tl"))
+    for red in ("mean", "sum", "none"):
+        loss, grad = _run_ours(lp, tgt, il, tl, red)
+        np.testing.assert_allclose(loss.numpy(), gold["loss_" + red], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(grad.numpy(), gold["grad_" + red], rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize(
+    "T,N,C,S,ragged",
+    [(201, 64, 97, 40, False), (201, 64, 97, 64, True), (257, 16, 97, 64, True), (50, 5, 11, 1, True), (33, 7, 5, 16, True), (300, 3, 97, 120, True), (520, 2, 30, 255, False)],
+)
+def test_vs_oracle(T, N, C, S, ragged):
+    g = torch.Generator().manual_seed(T * 1000 + N)
+    lp = torch.log_softmax(torch.randn(T, N, C, generator=g) * 2, dim=2)
+    tgt = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    tgt[:, 1::3] = tgt[:, 0::3][:, : tgt[:, 1::3].shape[1]]  # plenty of repeated labels
+    if ragged:
+        tl = torch.randint(0, S + 1, (N,), generator=g)
+        tl[0] = S
+        il = torch.randint(T // 2, T + 1, (N,), generator=g)
+        il[0] = T
+    else:
+        tl = torch.full((N,), S)
+        il = torch.full((N,), T - 1)
+    # keep every sample feasible: input length >= S + repeats
+    for n in range(N):
+        s = int(tl[n])
+        rep = int((tgt[n, 1:s] == tgt[n, : max(s - 1, 0)]).sum()) if s > 1 else 0
+        il[n] = max(int(il[n]), min(T, s + rep))
+    lo, go = _run_ours(lp, tgt, il, tl)
+    lr, gr = _run_oracle(lp, tgt, il, tl)
+    assert torch.isfinite(lr)
+    assert abs(lo - lr) <= 1e-5 * abs(lr), (lo, lr)
+    err = (go - gr).abs().max().item()
+    assert err <= 1e-5 * max(gr.abs().max().item(), 1e-3), err
+
+
+def test_infeasible_and_zero_infinity():
+    g = torch.Generator().manual_seed(3)
+    lp = torch.log_softmax(torch.randn(6, 2, 5, generator=g), dim=2)
+    tgt = torch.tensor([[1, 1, 1, 1], [2, 3, 0, 0]], dtype=torch.int32)
+    il, tl = torch.tensor([6, 6]), torch.tensor([4, 2])  # sample 0 needs 7 frames
+    lo, _ = _run_ours(lp, tgt, il, tl, "none")
+    assert torch.isinf(lo[0]) and torch.isfinite(lo[1])
+    lo, go = _run_ours(lp, tgt, il, tl, "sum", zero_infinity=True)
+    lr, gr = _run_oracle(lp, tgt, il, tl, "sum", zero_infinity=True)
+    assert abs(lo - lr) < 1e-5
+    torch.testing.assert_close(go, gr, rtol=1e-4, atol=1e-6)
+
+
+def test_numpy_restatement_agrees():
+    g = torch.Generator().manual_seed(5)
+    lp = torch.log_softmax(torch.randn(20, 1, 7, generator=g), dim=2)
+    tgt = torch.tensor([[3, 3, 1, 6, 2]], dtype=torch.int32)
+    lo, go = _run_ours(lp, tgt, torch.tensor([18]), torch.tensor([5]), "sum")
+    nll, grad = O.ctc_nll_numpy(lp[:, 0].numpy(), tgt[0].numpy(), 18)
+    assert abs(lo.item() - nll) < 1e-4
+    np.testing.assert_allclose(go[:, 0].numpy(), grad, atol=1e-5)
+
+
+def test_large_batch_property():
+    """N=8192 (the HBM-saturating shape): gradient rows sum to ~0 (softmax-folded convention)
+    and frames beyond input_length are exactly zero."""
+    T, N, C, S = 201, 8192, 97, 40
+    g = torch.Generator(device="cuda").manual_seed(1)
+    lp = torch.log_softmax(torch.randn(T, N, C, generator=g, device="cuda"), dim=2).requires_grad_(True)
+    tgt = torch.randint(1, C, (N, S), generator=g, device="cuda", dtype=torch.int32)
+    from ocrs_models_b200 import CTCLoss
+
+    loss = CTCLoss()(lp, tgt, torch.full((N,), 200), torch.full((N,), S))
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert lp.grad[200].abs().max().item() == 0.0
+    assert lp.grad[:200].sum(dim=2).abs().max().item() < 1e-6
+    # subsample against the oracle
+    idx = torch.arange(0, N, 1024)
+    lr, gr = _run_oracle(lp.detach()[:, idx].cpu(), tgt[idx].cpu(), torch.full((8,), 200), torch.full((8,), S), "sum")
+    ours = lp.grad[:, idx].cpu() * (N * S)
+    assert (ours - gr).abs().max().item() < 1e-4
