@@ -8,7 +8,7 @@ Drop-in surface (reference file:line in each module's docstring):
 * ``install()`` rebinds those names inside an imported ``ocrs_models`` so that its unmodified
   ``train_detection.py`` / ``train_rec.py`` run on the CUDA kernels.
 """
-from .losses import CTCLoss  # noqa: F401
+from .losses import CTCLoss, balanced_cross_entropy_loss  # noqa: F401
 from .models import DetectionModel, RecognitionModel  # noqa: F401
 
-__all__ = ["DetectionModel", "RecognitionModel", "CTCLoss"]
+__all__ = ["DetectionModel", "RecognitionModel", "CTCLoss", "balanced_cross_entropy_loss"]

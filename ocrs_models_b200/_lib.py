@@ -23,6 +23,35 @@ SIGNATURES: dict[str, list] = {
     "ocrs_ctc_alpha_row": [I],
     "ocrs_ctc_fwd": [P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P],
     "ocrs_ctc_bwd": [P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    # detection forward (csrc/det_fwd.cu)
+    "ocrs_det_dwpw_partial_rows": [I, I, I],
+    "ocrs_det_dwpw_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, P, P],
+    "ocrs_bn_finalize": [P, I, I, D, P, P, P, P, F, F, I, I, P, P, P, P, P, P],
+    "ocrs_det_pool2_fwd": [P, L, I, I, I, I, P, P, P, P, L, P],
+    "ocrs_det_convt_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, I, I, P],
+    "ocrs_det_outconv_fwd": [P, L, I, I, I, I, P, P, P, P, P, P, P],
+    # detection backward (csrc/det_bwd.cu)
+    "ocrs_finalize_partials": [P, I, I, P, P],
+    "ocrs_det_outconv_bwd_rows": [I, I, I],
+    "ocrs_det_outconv_bwd": [P, P, P, L, I, I, I, I, P, P, P, P, P, L, P, P],
+    "ocrs_reduce_rows": [I, L],
+    "ocrs_bnrelu_bwd_reduce": [P, L, P, L, I, I, L, P, P, P, P, P, P, P],
+    "ocrs_bn_bwd_finalize": [P, I, I, D, P, P, P, P, P, P, P, P, P],
+    "ocrs_det_pwT_bwd": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, I, P, L, P],
+    "ocrs_det_pw_wgrad_workers": [I, I, I],
+    "ocrs_det_pw_wgrad": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, L, I, P, P, P, P, P, P],
+    "ocrs_det_dw_bwd_rows": [I, I, I],
+    "ocrs_det_dw_bwd": [P, L, P, L, I, I, I, I, P, P, P, P, P, L, I, P, P],
+    "ocrs_det_pool2_bwd": [P, L, I, I, I, I, P, P, P, P, L, P, L, P],
+    "ocrs_det_convt_bwd_data": [P, L, I, I, I, I, P, I, I, I, P, L, P],
+    "ocrs_det_convt_wgrad_workers": [I, I, I],
+    "ocrs_det_convt_wgrad": [P, L, I, I, I, I, P, P, P, P, L, I, I, I, P, P],
+    "ocrs_plane_sum": [P, L, I, I, L, P, P],
+    # balanced BCE (csrc/det_loss.cu)
+    "ocrs_bce_state_words": [],
+    "ocrs_bce_blocks": [],
+    "ocrs_balanced_bce_fwd": [P, P, L, P, P, P, P, P],
+    "ocrs_balanced_bce_bwd": [P, P, P, L, P, P, P, P],
 }
 _RESTYPE = {"ocrs_last_error": c_char_p}
 

@@ -1,0 +1,729 @@
+// Backward kernels of the text-detection U-Net (autograd of reference ocrs_models/models.py:7-143).
+//
+// Per DepthwiseConv block (a = relu(bn(y)), y = pw(dw(xact))), given d_a:
+//   1. bnrelu_bwd_reduce  : per-channel  sum(dz), sum(dz * yhat)          (dz = d_a * [a > 0])
+//   2. bn_bwd_finalize    : d_gamma, d_beta and the affine  dy = k1*dz + k2*y + k3
+//   3. pwT_bwd            : g[ci]   = sum_co Wpw[co][ci] * dy[co]
+//   4. pw_wgrad           : dWpw[co][ci] = sum_p dy[co][p] * dwout[ci][p]   (dwout recomputed)
+//   5. dw_bwd             : d_xact = dw3x3^T(g),  dWdw[ci][k] = sum_p g[ci][p] * xact[ci][p+k]
+// Weight-gradient reductions over pixels are "skinny GEMMs" (M,N <= 16 per block, K = pixels):
+// operands are staged per 256-pixel tile in shared memory and each thread owns a 4x4 output
+// patch; per-block partial results are reduced in double by finalize_partials (deterministic).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_partials_kernel(const float* __restrict__ partials, int nblk, int K,
+                                         float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)partials[(size_t)b * K + k];
+  out[k] = (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out_conv backward: dz = dp * p * (1 - p); d_a[c] = w[c] * dz; partial sums of dz * a[c] and dz.
+__global__ void __launch_bounds__(256)
+outconv_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ prob,
+                   const float* __restrict__ x, long long x_ss, int C, long long HW,
+                   const float* __restrict__ sc, const float* __restrict__ sh,
+                   const float* __restrict__ lo, const float* __restrict__ w,
+                   float* __restrict__ d_a, long long da_ss, float* __restrict__ partials) {
+  __shared__ float red[32];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  const bool ok = i < HW;
+  float dz = 0.f;
+  if (ok) {
+    const float p = prob[(size_t)n * HW + i];
+    dz = dp[(size_t)n * HW + i] * p * (1.f - p);
+  }
+  const size_t blk = (size_t)n * gridDim.x + blockIdx.x;
+  for (int c = 0; c < C; ++c) {
+    float a = 0.f;
+    if (ok) {
+      a = x[(size_t)n * x_ss + (size_t)c * HW + i];
+      if (sc) a = xform_apply(a, sc[c], sh[c], lo[c]);
+      d_a[(size_t)n * da_ss + (size_t)c * HW + i] = w[c] * dz;
+    }
+    const float s = block_sum(a * dz, red);
+    if (threadIdx.x == 0) partials[blk * (C + 1) + c] = s;
+  }
+  const float s = block_sum(dz, red);
+  if (threadIdx.x == 0) partials[blk * (C + 1) + C] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm+ReLU backward, reduction half. grid = (chunks, C, N); partials [N*chunks][2][C].
+constexpr int RED_CHUNK = 4096;
+__global__ void __launch_bounds__(256)
+bnrelu_bwd_reduce_kernel(const float* __restrict__ d_a, long long da_ss,
+                         const float* __restrict__ y, long long y_ss, int C, long long HW,
+                         const float* __restrict__ sc, const float* __restrict__ sh,
+                         const float* __restrict__ lo, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, float* __restrict__ partials) {
+  __shared__ float red[32];
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float s = sc[c], t = sh[c], l = lo[c], mu = mean[c], is = invstd[c];
+  const float* dp = d_a + (size_t)n * da_ss + (size_t)c * HW;
+  const float* yp = y + (size_t)n * y_ss + (size_t)c * HW;
+  const long long i0 = (long long)blockIdx.x * RED_CHUNK;
+  const long long i1 = min(i0 + RED_CHUNK, HW);
+  float a = 0.f, b = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float yv = yp[i];
+    const float dz = (fmaf(yv, s, t) > l) ? dp[i] : 0.f;
+    a += dz;
+    b = fmaf(dz, (yv - mu) * is, b);
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) {
+    const size_t blk = (size_t)n * gridDim.x + blockIdx.x;
+    partials[blk * 2 * C + c] = a;
+    partials[blk * 2 * C + C + c] = b;
+  }
+}
+
+// d_gamma = sum dz*yhat, d_beta = sum dz; dy = k1*dz + k2*y + k3 with
+// k1 = gamma*invstd, k2 = -k1*invstd*d_gamma/M, k3 = -k1*d_beta/M - k2*mean.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int C,
+                                       double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ k1,
+                                       float* __restrict__ k2, float* __restrict__ k3) {
+  __shared__ double red[2][32];
+  const int c = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    a += (double)partials[(size_t)i * 2 * C + c];
+    b += (double)partials[(size_t)i * 2 * C + C + c];
+  }
+  a = warp_sum_d(a);
+  b = warp_sum_d(b);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  a = 0.0; b = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+  dbeta[c] = (float)a;
+  dgamma[c] = (float)b;
+  const double is = invstd[c], g1 = (double)gamma[c] * is;
+  const double g2 = -g1 * is * b / count;
+  k1[c] = (float)g1;
+  k2[c] = (float)g2;
+  k3[c] = (float)(-g1 * a / count - g2 * (double)mean[c]);
+}
+
+struct DyCoef {  // everything needed to rebuild dy[co] from (d_a, y) on the fly
+  const float *sc, *sh, *lo, *k1, *k2, *k3;
+};
+__device__ __forceinline__ float dy_of(float da, float yv, float s, float t, float l, float a1,
+                                       float a2, float a3) {
+  const float dz = (fmaf(yv, s, t) > l) ? da : 0.f;
+  return fmaf(a1, dz, fmaf(a2, yv, a3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// g[ci] = sum_co Wpw[co][ci] * dy[co]. Thread = VEC consecutive pixels, CI_T input channels.
+constexpr int PWT_CO_CHUNK = 16;
+template <int CI_T, int VEC>
+__global__ void __launch_bounds__(256)
+pwT_bwd_kernel(const float* __restrict__ d_a, long long da_ss, const float* __restrict__ y,
+               long long y_ss, int Cout, long long HW, DyCoef k, const float* __restrict__ wpw,
+               int Cin, float* __restrict__ g, long long g_ss) {
+  __shared__ __align__(16) float sw[PWT_CO_CHUNK * CI_T];
+  __shared__ float sk[6][PWT_CO_CHUNK];
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+  const int cig = (Cin + CI_T - 1) / CI_T;
+  const int ci0 = (blockIdx.y % cig) * CI_T, n = blockIdx.y / cig;
+  const bool ok = i < HW;
+  float acc[VEC][CI_T];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int c = 0; c < CI_T; ++c) acc[v][c] = 0.f;
+  for (int co0 = 0; co0 < Cout; co0 += PWT_CO_CHUNK) {
+    const int nco = min(PWT_CO_CHUNK, Cout - co0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < nco * CI_T; j += 256) {
+      const int o = j / CI_T, c = j - o * CI_T;
+      sw[j] = (ci0 + c < Cin) ? wpw[(size_t)(co0 + o) * Cin + ci0 + c] : 0.f;
+    }
+    if (threadIdx.x < nco) {
+      const int o = co0 + threadIdx.x;
+      sk[0][threadIdx.x] = k.sc[o]; sk[1][threadIdx.x] = k.sh[o]; sk[2][threadIdx.x] = k.lo[o];
+      sk[3][threadIdx.x] = k.k1[o]; sk[4][threadIdx.x] = k.k2[o]; sk[5][threadIdx.x] = k.k3[o];
+    }
+    __syncthreads();
+    if (!ok) continue;
+    for (int o = 0; o < nco; ++o) {
+      const float* dp = d_a + (size_t)n * da_ss + (size_t)(co0 + o) * HW + i;
+      const float* yp = y + (size_t)n * y_ss + (size_t)(co0 + o) * HW + i;
+      float dv[VEC], yv[VEC];
+      if (VEC == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(dp);
+        const float4 b = *reinterpret_cast<const float4*>(yp);
+        dv[0] = a.x; dv[VEC > 1 ? 1 : 0] = a.y; dv[VEC > 2 ? 2 : 0] = a.z; dv[VEC > 3 ? 3 : 0] = a.w;
+        yv[0] = b.x; yv[VEC > 1 ? 1 : 0] = b.y; yv[VEC > 2 ? 2 : 0] = b.z; yv[VEC > 3 ? 3 : 0] = b.w;
+      } else {
+        dv[0] = dp[0]; yv[0] = yp[0];
+      }
+      float dy[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        dy[v] = dy_of(dv[v], yv[v], sk[0][o], sk[1][o], sk[2][o], sk[3][o], sk[4][o], sk[5][o]);
+      const float4* w4 = reinterpret_cast<const float4*>(sw + o * CI_T);
+#pragma unroll
+      for (int c4 = 0; c4 < CI_T / 4; ++c4) {
+        const float4 wv = w4[c4];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          acc[v][c4 * 4 + 0] = fmaf(dy[v], wv.x, acc[v][c4 * 4 + 0]);
+          acc[v][c4 * 4 + 1] = fmaf(dy[v], wv.y, acc[v][c4 * 4 + 1]);
+          acc[v][c4 * 4 + 2] = fmaf(dy[v], wv.z, acc[v][c4 * 4 + 2]);
+          acc[v][c4 * 4 + 3] = fmaf(dy[v], wv.w, acc[v][c4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  if (!ok) return;
+#pragma unroll
+  for (int c = 0; c < CI_T; ++c) {
+    if (ci0 + c >= Cin) continue;
+    float* gp = g + (size_t)n * g_ss + (size_t)(ci0 + c) * HW + i;
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(gp) =
+          make_float4(acc[0][c], acc[VEC > 1 ? 1 : 0][c], acc[VEC > 2 ? 2 : 0][c], acc[VEC > 3 ? 3 : 0][c]);
+    } else {
+      gp[0] = acc[0][c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skinny GEMM core: sa/sb hold 256 pixels x 16 rows (row stride SG_LD floats). Thread t owns the
+// 4x4 patch (rows a: 4*((t&15)>>2).., rows b: 4*(t&3)..) over pixel slice t>>4 (16 pixels).
+constexpr int SG_LD = 20;
+__device__ __forceinline__ void skinny_accumulate(const float* sa, const float* sb, float acc[4][4]) {
+  const int t = threadIdx.x, slice = t >> 4, ab = (t & 15) >> 2, bb = t & 3;
+#pragma unroll 4
+  for (int pp = 0; pp < 16; ++pp) {
+    const int p = slice * 16 + pp;
+    const float4 a = *reinterpret_cast<const float4*>(sa + p * SG_LD + ab * 4);
+    const float4 b = *reinterpret_cast<const float4*>(sb + p * SG_LD + bb * 4);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+// Reduce the 16 pixel slices; thread t < 256 returns element (row a = t>>4, row b = t&15).
+__device__ __forceinline__ float skinny_reduce(float* scratch /* >= 16*256 floats */, float acc[4][4]) {
+  const int t = threadIdx.x, slice = t >> 4, ab = (t & 15) >> 2, bb = t & 3;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) scratch[slice * 256 + (ab * 4 + i) * 16 + bb * 4 + j] = acc[i][j];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int sl = 0; sl < 16; ++sl) s += scratch[sl * 256 + t];
+  return s;
+}
+
+// dWpw[co][ci] = sum_p dy[co][p] * dwout[ci][p], dwout = dw3x3(xform(x)) recomputed per tile.
+// grid = (workers, co_tiles * ci_tiles); tile = 32x8 pixels of one image.
+constexpr int WG_TW = 32, WG_TH = 8, WG_SROW = WG_TW + 2, WG_SPLANE = (WG_TH + 2) * WG_SROW;
+constexpr int WG_SMEM_FLOATS = 16 * WG_SPLANE + 2 * 256 * SG_LD;
+__global__ void __launch_bounds__(256)
+pw_wgrad_kernel(const float* __restrict__ d_a, long long da_ss, const float* __restrict__ y,
+                long long y_ss, int Cout, DyCoef k, const float* __restrict__ x, long long x_ss,
+                int Cin, int H, int W, const float* __restrict__ isc, const float* __restrict__ ish,
+                const float* __restrict__ ilo, const float* __restrict__ wdw, int N, int tiles_x,
+                int tiles_y, float* __restrict__ partials) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                      // [16][WG_SPLANE]
+  float* sa = smem + 16 * WG_SPLANE;     // dy    [256][SG_LD]
+  float* sb = sa + 256 * SG_LD;          // dwout [256][SG_LD]
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int cit = (Cin + 15) / 16;
+  const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
+  const int nco = min(16, Cout - co0), nci = min(16, Cin - ci0);
+  const size_t HW = (size_t)H * W;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int tiles = tiles_x * tiles_y;
+  const long long total = (long long)N * tiles;
+  for (long long work = blockIdx.x; work < total; work += gridDim.x) {
+    const int n = (int)(work / tiles), tile = (int)(work % tiles);
+    const int x0 = (tile % tiles_x) * WG_TW, y0 = (tile / tiles_x) * WG_TH;
+    __syncthreads();
+    for (int i = tid; i < nci * WG_SPLANE; i += 256) {
+      const int c = i / WG_SPLANE, r = i - c * WG_SPLANE;
+      const int ry = r / WG_SROW, rx = r - ry * WG_SROW;
+      const int gy = y0 + ry - 1, gx = x0 + rx - 1;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        v = x[(size_t)n * x_ss + (size_t)(ci0 + c) * HW + (size_t)gy * W + gx];
+        if (isc) v = xform_apply(v, isc[ci0 + c], ish[ci0 + c], ilo[ci0 + c]);
+      }
+      xs[i] = v;
+    }
+    // dy for this thread's pixel
+    const int gy = y0 + ty, gx = x0 + tx;
+    const bool ok = gy < H && gx < W;
+    float va[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      float v = 0.f;
+      if (ok && o < nco) {
+        const size_t off = (size_t)(co0 + o) * HW + (size_t)gy * W + gx;
+        v = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], k.sc[co0 + o],
+                  k.sh[co0 + o], k.lo[co0 + o], k.k1[co0 + o], k.k2[co0 + o], k.k3[co0 + o]);
+      }
+      va[o] = v;
+    }
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4)
+      *reinterpret_cast<float4*>(sa + tid * SG_LD + o4 * 4) =
+          make_float4(va[o4 * 4], va[o4 * 4 + 1], va[o4 * 4 + 2], va[o4 * 4 + 3]);
+    __syncthreads();
+    float vb[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float s = 0.f;
+      if (ok && c < nci) {
+        const float* t = xs + c * WG_SPLANE + ty * WG_SROW + tx;
+        const float* wk = wdw + (size_t)(ci0 + c) * 9;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) s = fmaf(t[ky * WG_SROW + kx], __ldg(wk + ky * 3 + kx), s);
+      }
+      vb[c] = s;
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+      *reinterpret_cast<float4*>(sb + tid * SG_LD + c4 * 4) =
+          make_float4(vb[c4 * 4], vb[c4 * 4 + 1], vb[c4 * 4 + 2], vb[c4 * 4 + 3]);
+    __syncthreads();
+    skinny_accumulate(sa, sb, acc);
+  }
+  const float s = skinny_reduce(smem, acc);
+  const int o = tid >> 4, c = tid & 15;
+  // partial layout: [worker][Cout][Cin]
+  if (o < nco && c < nci)
+    partials[((size_t)blockIdx.x * Cout + co0 + o) * Cin + ci0 + c] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise 3x3 backward for one channel plane tile: d_x = corr(g, flip(w)); dW[k] partials.
+constexpr int DW_TH = 32;
+__global__ void __launch_bounds__(256)
+dw_bwd_kernel(const float* __restrict__ g, long long g_ss, const float* __restrict__ x,
+              long long x_ss, int C, int H, int W, const float* __restrict__ isc,
+              const float* __restrict__ ish, const float* __restrict__ ilo,
+              const float* __restrict__ wdw, float* __restrict__ dx, long long dx_ss,
+              int accumulate, float* __restrict__ partials, int tiles_x) {
+  __shared__ float gs[(DW_TH + 2) * 34];
+  __shared__ float xs[(DW_TH + 2) * 34];
+  __shared__ float red[8][9];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int tile = blockIdx.x, c = blockIdx.y, n = blockIdx.z;
+  const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * DW_TH;
+  const size_t HW = (size_t)H * W;
+  const float* gp = g + (size_t)n * g_ss + (size_t)c * HW;
+  const float* xp = x + (size_t)n * x_ss + (size_t)c * HW;
+  const bool need_x = partials != nullptr;
+  float s = 1.f, t = 0.f, l = -INFINITY;
+  if (isc) { s = isc[c]; t = ish[c]; l = ilo[c]; }
+  for (int i = tid; i < (DW_TH + 2) * 34; i += 256) {
+    const int ry = i / 34, rx = i - ry * 34;
+    const int gy = y0 + ry - 1, gx = x0 + rx - 1;
+    float gv = 0.f, xv = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      gv = gp[(size_t)gy * W + gx];
+      if (need_x) {
+        xv = xp[(size_t)gy * W + gx];
+        if (isc) xv = xform_apply(xv, s, t, l);
+      }
+    }
+    gs[i] = gv;
+    xs[i] = xv;
+  }
+  float w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = wdw[(size_t)c * 9 + k];
+  __syncthreads();
+  float dw[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dw[k] = 0.f;
+  float* dxp = dx + (size_t)n * dx_ss + (size_t)c * HW;
+#pragma unroll
+  for (int p = 0; p < DW_TH / 8; ++p) {
+    const int ly = ty * (DW_TH / 8) + p, gy = y0 + ly, gx = x0 + tx;
+    if (gy < H && gx < W) {
+      float v = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) v = fmaf(w[ky * 3 + kx], gs[(ly + 2 - ky) * 34 + tx + 2 - kx], v);
+      const size_t off = (size_t)gy * W + gx;
+      dxp[off] = accumulate ? dxp[off] + v : v;
+      if (need_x) {
+        const float gc = gs[(ly + 1) * 34 + tx + 1];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) dw[ky * 3 + kx] = fmaf(gc, xs[(ly + ky) * 34 + tx + kx], dw[ky * 3 + kx]);
+      }
+    }
+  }
+  if (!need_x) return;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float v = warp_sum(dw[k]);
+    if (tx == 0) red[ty][k] = v;
+  }
+  __syncthreads();
+  if (tid < 9) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += red[q][tid];
+    const size_t blk = (size_t)n * gridDim.x + tile;
+    partials[(blk * C + c) * 9 + tid] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(2) backward: thread per full-resolution pixel; gradient goes to the first maximum
+// of its 2x2 window (aten's tie rule), zero elsewhere and in a trailing odd row/column.
+__global__ void pool2_bwd_kernel(const float* __restrict__ x, long long x_ss, int C, int H, int W,
+                                 const float* __restrict__ sc, const float* __restrict__ sh,
+                                 const float* __restrict__ lo, const float* __restrict__ dout,
+                                 long long dout_ss, float* __restrict__ din, long long din_ss) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int c = blockIdx.z % C, n = blockIdx.z / C;
+  if (ix >= W || iy >= H) return;
+  const int Ho = H / 2, Wo = W / 2, oy = iy >> 1, ox = ix >> 1;
+  float r = 0.f;
+  if (oy < Ho && ox < Wo) {
+    const float* p = x + (size_t)n * x_ss + (size_t)c * H * W + (size_t)(2 * oy) * W + 2 * ox;
+    float v[4] = {p[0], p[1], p[W], p[W + 1]};
+    if (sc) {
+      const float s = sc[c], t = sh[c], l = lo[c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = xform_apply(v[q], s, t, l);
+    }
+    int am = 0;
+    float m = v[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if (v[q] > m || isnan(v[q])) { m = v[q]; am = q; }
+    if (am == (iy & 1) * 2 + (ix & 1))
+      r = dout[(size_t)n * dout_ss + (size_t)c * Ho * Wo + (size_t)oy * Wo + ox];
+  }
+  din[(size_t)n * din_ss + (size_t)c * H * W + (size_t)iy * W + ix] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose2d backward (data): d_x[ci][iy][ix] = sum_co,k W[ci][co][k] * d_out[co][2iy+ky][2ix+kx].
+template <int CI_T>
+__global__ void __launch_bounds__(256)
+convt_bwd_data_kernel(const float* __restrict__ dout, long long dout_ss, int Cout, int Hs, int Ws,
+                      const float* __restrict__ w, int Cin, int Hin, int Win,
+                      float* __restrict__ dx, long long dx_ss) {
+  __shared__ __align__(16) float sw[8 * 9 * CI_T];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int ix = blockIdx.x * 32 + threadIdx.x, iy = blockIdx.y * 8 + threadIdx.y;
+  const int cig = (Cin + CI_T - 1) / CI_T;
+  const int ci0 = (blockIdx.z % cig) * CI_T, n = blockIdx.z / cig;
+  const bool ok = ix < Win && iy < Hin;
+  const size_t HWs = (size_t)Hs * Ws;
+  float acc[CI_T];
+#pragma unroll
+  for (int c = 0; c < CI_T; ++c) acc[c] = 0.f;
+  for (int co0 = 0; co0 < Cout; co0 += 8) {
+    const int nco = min(8, Cout - co0);
+    __syncthreads();
+    for (int i = tid; i < nco * 9 * CI_T; i += 256) {
+      const int o = i / (9 * CI_T), r = i - o * 9 * CI_T, kk = r / CI_T, c = r - kk * CI_T;
+      sw[i] = (ci0 + c < Cin) ? w[((size_t)(ci0 + c) * Cout + co0 + o) * 9 + kk] : 0.f;
+    }
+    __syncthreads();
+    if (!ok) continue;
+    for (int o = 0; o < nco; ++o) {
+      const float* dp = dout + (size_t)n * dout_ss + (size_t)(co0 + o) * HWs;
+      float d[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int oy = 2 * iy + ky, ox = 2 * ix + kx;
+          d[ky * 3 + kx] = (oy < Hs && ox < Ws) ? dp[(size_t)oy * Ws + ox] : 0.f;
+        }
+      const float* wo = sw + o * 9 * CI_T;
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk)
+#pragma unroll
+        for (int c = 0; c < CI_T; ++c) acc[c] = fmaf(d[kk], wo[kk * CI_T + c], acc[c]);
+    }
+  }
+  if (!ok) return;
+#pragma unroll
+  for (int c = 0; c < CI_T; ++c)
+    if (ci0 + c < Cin)
+      dx[(size_t)n * dx_ss + (size_t)(ci0 + c) * Hin * Win + (size_t)iy * Win + ix] = acc[c];
+}
+
+// ConvTranspose2d weight gradient: dW[ci][co][k] = sum_p xact[ci][p] * d_out[co][2iy+ky][2ix+kx].
+// Rows a = 16 input channels, rows b = 16 of the Cout*9 (co, tap) pairs. grid = (workers, tiles).
+__global__ void __launch_bounds__(256)
+convt_wgrad_kernel(const float* __restrict__ x, long long x_ss, int Cin, int Hin, int Win,
+                   const float* __restrict__ isc, const float* __restrict__ ish,
+                   const float* __restrict__ ilo, const float* __restrict__ dout,
+                   long long dout_ss, int Cout, int Hs, int Ws, int N, float* __restrict__ partials) {
+  __shared__ __align__(16) float smem[2 * 256 * SG_LD];
+  float* sa = smem;
+  float* sb = smem + 256 * SG_LD;
+  const int tid = threadIdx.x;
+  const int CK = Cout * 9;
+  const int bt = (CK + 15) / 16;
+  const int ci0 = (blockIdx.y / bt) * 16, b0 = (blockIdx.y % bt) * 16;
+  const int nci = min(16, Cin - ci0), nb = min(16, CK - b0);
+  const size_t HWi = (size_t)Hin * Win, HWs = (size_t)Hs * Ws;
+  const long long total = (long long)N * HWi;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long base = (long long)blockIdx.x * 256; base < total; base += (long long)gridDim.x * 256) {
+    const long long pidx = base + tid;
+    const bool ok = pidx < total;
+    const int n = ok ? (int)(pidx / HWi) : 0;
+    const int rem = ok ? (int)(pidx % HWi) : 0;
+    const int iy = rem / Win, ix = rem - iy * Win;
+    float va[16], vb[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float v = 0.f;
+      if (ok && c < nci) {
+        v = x[(size_t)n * x_ss + (size_t)(ci0 + c) * HWi + rem];
+        if (isc) v = xform_apply(v, isc[ci0 + c], ish[ci0 + c], ilo[ci0 + c]);
+      }
+      va[c] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = 0.f;
+      if (ok && j < nb) {
+        const int co = (b0 + j) / 9, kk = (b0 + j) - co * 9, ky = kk / 3, kx = kk - ky * 3;
+        const int oy = 2 * iy + ky, ox = 2 * ix + kx;
+        if (oy < Hs && ox < Ws) v = dout[(size_t)n * dout_ss + (size_t)co * HWs + (size_t)oy * Ws + ox];
+      }
+      vb[j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      *reinterpret_cast<float4*>(sa + tid * SG_LD + q * 4) = make_float4(va[q * 4], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
+      *reinterpret_cast<float4*>(sb + tid * SG_LD + q * 4) = make_float4(vb[q * 4], vb[q * 4 + 1], vb[q * 4 + 2], vb[q * 4 + 3]);
+    }
+    __syncthreads();
+    skinny_accumulate(sa, sb, acc);
+  }
+  const float s = skinny_reduce(smem, acc);
+  const int c = tid >> 4, j = tid & 15;
+  // partial layout [worker][Cin][Cout*9] == weight layout [Cin][Cout][3][3]
+  if (c < nci && j < nb) partials[((size_t)blockIdx.x * Cin + ci0 + c) * CK + b0 + j] = s;
+}
+
+// Per-channel sum of a view over (N, H*W): ConvTranspose2d bias gradient. partials [N*chunks][C].
+__global__ void __launch_bounds__(256)
+plane_sum_kernel(const float* __restrict__ v, long long v_ss, int C, long long HW,
+                 float* __restrict__ partials) {
+  __shared__ float red[32];
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float* p = v + (size_t)n * v_ss + (size_t)c * HW;
+  const long long i0 = (long long)blockIdx.x * RED_CHUNK, i1 = min(i0 + RED_CHUNK, HW);
+  float a = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) a += p[i];
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) partials[((size_t)n * gridDim.x + blockIdx.x) * C + c] = a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ocrs_finalize_partials(const float* partials, int nblk, int K, float* out, void* stream) {
+  finalize_partials_kernel<<<ocrs_cdiv(K, 128), 128, 0, (cudaStream_t)stream>>>(partials, nblk, K, out);
+  OCRS_CHECK_LAUNCH("finalize_partials_kernel");
+  return 0;
+}
+
+int ocrs_det_outconv_bwd_rows(int N, int H, int W) { return N * ocrs_cdiv((long long)H * W, 256); }
+// partials: [rows][C+1] (dW[0..C), db)
+int ocrs_det_outconv_bwd(const float* dp, const float* prob, const float* x, long long x_ss, int N,
+                         int C, int H, int W, const float* sc, const float* sh, const float* lo,
+                         const float* w, float* d_a, long long da_ss, float* partials, void* stream) {
+  const long long HW = (long long)H * W;
+  dim3 grid(ocrs_cdiv(HW, 256), N);
+  outconv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dp, prob, x, x_ss, C, HW, sc, sh, lo, w,
+                                                             d_a, da_ss, partials);
+  OCRS_CHECK_LAUNCH("outconv_bwd_kernel");
+  return 0;
+}
+
+int ocrs_reduce_rows(int N, long long HW) { return N * ocrs_cdiv(HW, RED_CHUNK); }
+
+// partials: [ocrs_reduce_rows][2][C]
+int ocrs_bnrelu_bwd_reduce(const float* d_a, long long da_ss, const float* y, long long y_ss, int N,
+                           int C, long long HW, const float* sc, const float* sh, const float* lo,
+                           const float* mean, const float* invstd, float* partials, void* stream) {
+  dim3 grid(ocrs_cdiv(HW, RED_CHUNK), C, N);
+  bnrelu_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, C, HW, sc, sh,
+                                                                   lo, mean, invstd, partials);
+  OCRS_CHECK_LAUNCH("bnrelu_bwd_reduce_kernel");
+  return 0;
+}
+
+int ocrs_bn_bwd_finalize(const float* partials, int nblk, int C, double count, const float* gamma,
+                         const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                         float* k1, float* k2, float* k3, void* stream) {
+  bn_bwd_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(partials, nblk, C, count, gamma, mean,
+                                                              invstd, dgamma, dbeta, k1, k2, k3);
+  OCRS_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return 0;
+}
+
+int ocrs_det_pwT_bwd(const float* d_a, long long da_ss, const float* y, long long y_ss, int N,
+                     int Cout, long long HW, const float* sc, const float* sh, const float* lo,
+                     const float* k1, const float* k2, const float* k3, const float* wpw, int Cin,
+                     float* g, long long g_ss, void* stream) {
+  DyCoef k{sc, sh, lo, k1, k2, k3};
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (HW % 4 == 0) && (da_ss % 4 == 0) && (y_ss % 4 == 0) && (g_ss % 4 == 0) &&
+                   ((uintptr_t)d_a % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0);
+  const int cit = Cin <= 8 ? 8 : 16;
+  const int cig = ocrs_cdiv(Cin, cit);
+  if (vec) {
+    dim3 grid(ocrs_cdiv(HW, 1024), N * cig);
+    if (cit == 8)
+      pwT_bwd_kernel<8, 4><<<grid, 256, 0, st>>>(d_a, da_ss, y, y_ss, Cout, HW, k, wpw, Cin, g, g_ss);
+    else
+      pwT_bwd_kernel<16, 4><<<grid, 256, 0, st>>>(d_a, da_ss, y, y_ss, Cout, HW, k, wpw, Cin, g, g_ss);
+  } else {
+    dim3 grid(ocrs_cdiv(HW, 256), N * cig);
+    if (cit == 8)
+      pwT_bwd_kernel<8, 1><<<grid, 256, 0, st>>>(d_a, da_ss, y, y_ss, Cout, HW, k, wpw, Cin, g, g_ss);
+    else
+      pwT_bwd_kernel<16, 1><<<grid, 256, 0, st>>>(d_a, da_ss, y, y_ss, Cout, HW, k, wpw, Cin, g, g_ss);
+  }
+  OCRS_CHECK_LAUNCH("pwT_bwd_kernel");
+  return 0;
+}
+
+int ocrs_det_pw_wgrad_workers(int N, int H, int W) {
+  const long long tiles = (long long)N * ocrs_cdiv(W, WG_TW) * ocrs_cdiv(H, WG_TH);
+  return (int)(tiles < 2 * OCRS_NUM_SMS ? tiles : 2 * OCRS_NUM_SMS);
+}
+// partials: [workers][Cout][Cin]; must be zero-filled when Cout or Cin is not a multiple of 16? no:
+// every (co, ci) element is written by exactly one block column.
+int ocrs_det_pw_wgrad(const float* d_a, long long da_ss, const float* y, long long y_ss, int N,
+                      int Cout, int H, int W, const float* sc, const float* sh, const float* lo,
+                      const float* k1, const float* k2, const float* k3, const float* x,
+                      long long x_ss, int Cin, const float* isc, const float* ish, const float* ilo,
+                      const float* wdw, float* partials, void* stream) {
+  static bool attr_set = false;
+  const size_t smem = WG_SMEM_FLOATS * sizeof(float);
+  if (!attr_set) {
+    OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  DyCoef k{sc, sh, lo, k1, k2, k3};
+  const int tiles_x = ocrs_cdiv(W, WG_TW), tiles_y = ocrs_cdiv(H, WG_TH);
+  dim3 grid(ocrs_det_pw_wgrad_workers(N, H, W), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
+  pw_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin,
+                                                            H, W, isc, ish, ilo, wdw, N, tiles_x,
+                                                            tiles_y, partials);
+  OCRS_CHECK_LAUNCH("pw_wgrad_kernel");
+  return 0;
+}
+
+int ocrs_det_dw_bwd_rows(int N, int H, int W) { return N * ocrs_cdiv(W, 32) * ocrs_cdiv(H, DW_TH); }
+// partials: [rows][C][9] or NULL to skip the weight gradient (and the read of x).
+int ocrs_det_dw_bwd(const float* g, long long g_ss, const float* x, long long x_ss, int N, int C, int H,
+                    int W, const float* isc, const float* ish, const float* ilo, const float* wdw,
+                    float* dx, long long dx_ss, int accumulate, float* partials, void* stream) {
+  const int tiles_x = ocrs_cdiv(W, 32), tiles_y = ocrs_cdiv(H, DW_TH);
+  dim3 grid(tiles_x * tiles_y, C, N);
+  dw_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, g_ss, x, x_ss, C, H, W, isc, ish, ilo, wdw, dx,
+                                                        dx_ss, accumulate, partials, tiles_x);
+  OCRS_CHECK_LAUNCH("dw_bwd_kernel");
+  return 0;
+}
+
+int ocrs_det_pool2_bwd(const float* x, long long x_ss, int N, int C, int H, int W, const float* sc,
+                       const float* sh, const float* lo, const float* dout, long long dout_ss,
+                       float* din, long long din_ss, void* stream) {
+  dim3 block(32, 8), grid(ocrs_cdiv(W, 32), ocrs_cdiv(H, 8), N * C);
+  pool2_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, dout, dout_ss,
+                                                             din, din_ss);
+  OCRS_CHECK_LAUNCH("pool2_bwd_kernel");
+  return 0;
+}
+
+int ocrs_det_convt_bwd_data(const float* dout, long long dout_ss, int N, int Cout, int Hs, int Ws,
+                            const float* w, int Cin, int Hin, int Win, float* dx, long long dx_ss,
+                            void* stream) {
+  dim3 block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin <= 8) {
+    dim3 grid(ocrs_cdiv(Win, 32), ocrs_cdiv(Hin, 8), N * ocrs_cdiv(Cin, 8));
+    convt_bwd_data_kernel<8><<<grid, block, 0, st>>>(dout, dout_ss, Cout, Hs, Ws, w, Cin, Hin, Win, dx, dx_ss);
+  } else {
+    dim3 grid(ocrs_cdiv(Win, 32), ocrs_cdiv(Hin, 8), N * ocrs_cdiv(Cin, 16));
+    convt_bwd_data_kernel<16><<<grid, block, 0, st>>>(dout, dout_ss, Cout, Hs, Ws, w, Cin, Hin, Win, dx, dx_ss);
+  }
+  OCRS_CHECK_LAUNCH("convt_bwd_data_kernel");
+  return 0;
+}
+
+int ocrs_det_convt_wgrad_workers(int N, int Hin, int Win) {
+  const long long blocks = ((long long)N * Hin * Win + 255) / 256;
+  return (int)(blocks < 2 * OCRS_NUM_SMS ? blocks : 2 * OCRS_NUM_SMS);
+}
+// partials: [workers][Cin][Cout][9]
+int ocrs_det_convt_wgrad(const float* x, long long x_ss, int N, int Cin, int Hin, int Win,
+                         const float* isc, const float* ish, const float* ilo, const float* dout,
+                         long long dout_ss, int Cout, int Hs, int Ws, float* partials, void* stream) {
+  dim3 grid(ocrs_det_convt_wgrad_workers(N, Hin, Win), ocrs_cdiv(Cin, 16) * ocrs_cdiv(Cout * 9, 16));
+  convt_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout,
+                                                             dout_ss, Cout, Hs, Ws, N, partials);
+  OCRS_CHECK_LAUNCH("convt_wgrad_kernel");
+  return 0;
+}
+
+// partials: [ocrs_reduce_rows(N, HW)][C]
+int ocrs_plane_sum(const float* v, long long v_ss, int N, int C, long long HW, float* partials,
+                   void* stream) {
+  dim3 grid(ocrs_cdiv(HW, RED_CHUNK), C, N);
+  plane_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(v, v_ss, C, HW, partials);
+  OCRS_CHECK_LAUNCH("plane_sum_kernel");
+  return 0;
+}
+
+}  // extern "C"

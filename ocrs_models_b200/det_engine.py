@@ -1,0 +1,320 @@
+"""Execution plan of the detection U-Net on the sm_100a kernels (csrc/det_fwd.cu, det_bwd.cu).
+
+Follows reference ``DetectionModel.forward`` (ocrs_models/models.py:131-143) op for op, but:
+
+* activations are planar NCHW fp32 *views* (tensor, element offset, per-sample stride), so the
+  ``torch.cat`` of ``Up.forward`` (models.py:89) is two producers writing into one buffer;
+* BatchNorm+ReLU of a block is folded into the loads of its consumers (per-channel scale/shift/lo);
+* the whole forward is one ``torch.autograd.Function`` whose backward runs the hand-written
+  backward kernels and returns every parameter gradient.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+NEG_INF = float("-inf")
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class View:
+    """Planar NCHW fp32 view: channel stride is H*W, sample stride `ss`, optional load transform."""
+
+    __slots__ = ("t", "off", "ss", "C", "H", "W", "xf")
+
+    def __init__(self, t, off, ss, C, H, W, xf=None):
+        self.t, self.off, self.ss, self.C, self.H, self.W, self.xf = t, off, ss, C, H, W, xf
+
+    @property
+    def p(self):
+        return self.t.data_ptr() + 4 * self.off
+
+    def xfp(self):
+        if self.xf is None:
+            return (None, None, None)
+        return tuple(a.data_ptr() for a in self.xf)
+
+    def chan(self, c0, c1):
+        xf = None if self.xf is None else tuple(a[c0:c1] for a in self.xf)
+        return View(self.t, self.off + c0 * self.H * self.W, self.ss, c1 - c0, self.H, self.W, xf)
+
+
+def new_view(N, C, H, W, dev, xf=None):
+    t = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+    return View(t, 0, C * H * W, C, H, W, xf)
+
+
+def _finalize(partials, nblk, K, out, st):
+    call("ocrs_finalize_partials", ptr(partials), nblk, K, ptr(out), st)
+
+
+class _Sep:
+    """One DepthwiseConv block (models.py:7-28): parameters + what backward needs."""
+
+    def __init__(self, mod):
+        self.dw, self.pw, self.bn = mod.seq[0], mod.seq[1], mod.seq[2]
+        self.cin, self.cout = self.pw.in_channels, self.pw.out_channels
+
+    def params(self):
+        return [self.dw.weight, self.pw.weight, self.bn.weight, self.bn.bias]
+
+    def forward(self, inp: View, N, training, st, y: View | None = None, xf_dst=None, save=None):
+        """`save`: dict that receives this block's backward record (keyed by id(self)), or None."""
+        dev = inp.t.device
+        H, W = inp.H, inp.W
+        if y is None:
+            y = new_view(N, self.cout, H, W, dev)
+        lib = _lib.lib()
+        rows = lib.ocrs_det_dwpw_partial_rows(N, H, W)
+        partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
+        call("ocrs_det_dwpw_fwd", inp.p, inp.ss, N, self.cin, H, W, *inp.xfp(), ptr(self.dw.weight),
+             ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st)
+        if xf_dst is None:
+            buf = torch.empty((3, self.cout), dtype=torch.float32, device=dev)
+            xf_dst = (buf[0], buf[1], buf[2])
+        stats = torch.empty((2, self.cout), dtype=torch.float32, device=dev)
+        bn = self.bn
+        call("ocrs_bn_finalize", ptr(partials), rows, self.cout, float(N * H * W), ptr(bn.weight), ptr(bn.bias),
+             ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, int(training), 1,
+             xf_dst[0].data_ptr(), xf_dst[1].data_ptr(), xf_dst[2].data_ptr(), ptr(stats[0]), ptr(stats[1]), st)
+        if training:
+            bn.num_batches_tracked.add_(1)
+        y.xf = xf_dst
+        if save is not None:
+            save[id(self)] = (inp, y, stats)
+        return y
+
+    def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False):
+        """d_a: gradient w.r.t. this block's activated output. Writes the gradient w.r.t. the
+        block's (activated) input into `dx`; returns [d_wdw, d_wpw, d_gamma, d_beta]."""
+        inp, y, stats = saved.pop(id(self))
+        dev = y.t.device
+        lib = _lib.lib()
+        H, W, HW = y.H, y.W, y.H * y.W
+        co, ci = self.cout, self.cin
+        rows = lib.ocrs_reduce_rows(N, HW)
+        part = torch.empty((rows, 2, co), dtype=torch.float32, device=dev)
+        ysc, ysh, ylo = y.xfp()
+        call("ocrs_bnrelu_bwd_reduce", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, ysc, ysh, ylo, ptr(stats[0]),
+             ptr(stats[1]), ptr(part), st)
+        coef = torch.empty((5, co), dtype=torch.float32, device=dev)  # dgamma, dbeta, k1, k2, k3
+        call("ocrs_bn_bwd_finalize", ptr(part), rows, co, float(N * HW), ptr(self.bn.weight), ptr(stats[0]),
+             ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), st)
+        k = (ysc, ysh, ylo, ptr(coef[2]), ptr(coef[3]), ptr(coef[4]))
+        g = new_view(N, ci, H, W, dev)
+        call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st)
+        workers = lib.ocrs_det_pw_wgrad_workers(N, H, W)
+        wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+        call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
+             ptr(self.dw.weight), ptr(wpart), st)
+        d_wpw = torch.empty_like(self.pw.weight)
+        _finalize(wpart, workers, co * ci, d_wpw, st)
+        drows = lib.ocrs_det_dw_bwd_rows(N, H, W)
+        dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
+        if dx is None:
+            dx = new_view(N, ci, H, W, dev)
+        call("ocrs_det_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
+             dx.ss, int(accumulate), ptr(dpart), st)
+        d_wdw = torch.empty_like(self.dw.weight)
+        _finalize(dpart, drows, ci * 9, d_wdw, st)
+        return [d_wdw, d_wpw, coef[0].clone(), coef[1].clone()], dx
+
+
+class _Plan:
+    """Static description of the network built from the module tree (parameter order included)."""
+
+    def __init__(self, model):
+        self.model = model
+        d = model.depth_scale
+        self.levels = len(d) - 1
+        self.in_conv = [_Sep(model.in_conv.seq[0]), _Sep(model.in_conv.seq[1])]
+        self.down = [[_Sep(m.seq[0].seq[0]), _Sep(m.seq[0].seq[1])] for m in model.down]
+        self.upT = [m.up for m in model.up]
+        self.contract = [[_Sep(m.contract.seq[0]), _Sep(m.contract.seq[1])] for m in model.up]
+        self.out = model.out_conv[0]
+        self.depth = d
+
+    def all_params(self):
+        ps = []
+        for s in self.in_conv:
+            ps += s.params()
+        for pair in self.down:
+            for s in pair:
+                ps += s.params()
+        for i in range(self.levels):
+            ps += [self.upT[i].weight, self.upT[i].bias]
+            for s in self.contract[i]:
+                ps += s.params()
+        ps += [self.out.weight, self.out.bias]
+        return ps
+
+
+def _identity_xf(C, dev):
+    buf = torch.empty((3, C), dtype=torch.float32, device=dev)
+    buf[0].fill_(1.0)
+    buf[1].zero_()
+    buf[2].fill_(NEG_INF)
+    return (buf[0], buf[1], buf[2])
+
+
+class _DetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: _Plan, x, *params):
+        model = plan.model
+        training = model.training
+        dev = x.device
+        N, _, H, W = x.shape
+        d = plan.depth
+        L = plan.levels
+        st = _lib.stream_ptr(dev)
+        save = {} if any(ctx.needs_input_grad) else None
+        xin = View(x, 0, H * W, 1, H, W)
+        # resolution of each level: level 0 = input size, level i = floor(level i-1 / 2)
+        hs, ws = [H], [W]
+        for i in range(L):
+            hs.append(hs[-1] // 2)
+            ws.append(ws[-1] // 2)
+        if hs[L] < 1 or ws[L] < 1:
+            raise RuntimeError(f"DetectionModel needs inputs of at least {2**L}x{2**L}, got {H}x{W}")
+        # concat buffers of the six Up stages: [ConvT output | skip]
+        cat = [torch.empty((N, 2 * d[i], hs[i], ws[i]), dtype=torch.float32, device=dev) for i in range(L)]
+        catxf = [_identity_xf(2 * d[i], dev) for i in range(L)]
+
+        def cat_view(i, lo, hi):
+            xf = tuple(a[lo:hi] for a in catxf[i])
+            return View(cat[i], lo * hs[i] * ws[i], 2 * d[i] * hs[i] * ws[i], hi - lo, hs[i], ws[i], xf)
+
+        with torch.cuda.device(dev):
+            a = plan.in_conv[0].forward(xin, N, training, st, save=save)
+            # in_conv output (raw + its BN transform) lives in the skip half of cat[0]
+            skip0 = cat_view(0, d[0], 2 * d[0])
+            xfull = plan.in_conv[1].forward(a, N, training, st, y=skip0, xf_dst=skip0.xf, save=save)
+            prev = xfull
+            pooled_src = []
+            for i in range(L):
+                a = plan.down[i][0].forward(prev, N, training, st, save=save)
+                b = plan.down[i][1].forward(a, N, training, st, save=save)
+                if i + 1 < L:
+                    dst = cat_view(i + 1, d[i + 1], 2 * d[i + 1])
+                else:
+                    dst = new_view(N, d[L], hs[L], ws[L], dev, _identity_xf(d[L], dev))
+                call("ocrs_det_pool2_fwd", b.p, b.ss, N, b.C, b.H, b.W, *b.xfp(), dst.p, dst.ss, st)
+                pooled_src.append(b)
+                prev = dst
+            up = prev
+            up_inputs = []
+            for i in reversed(range(L)):
+                t = plan.upT[i]
+                lo_half = cat_view(i, 0, d[i])
+                call("ocrs_det_convt_fwd", up.p, up.ss, N, up.C, up.H, up.W, *up.xfp(), ptr(t.weight), ptr(t.bias),
+                     d[i], lo_half.p, lo_half.ss, hs[i], ws[i], st)
+                up_inputs.append((i, up))
+                full = cat_view(i, 0, 2 * d[i])
+                a = plan.contract[i][0].forward(full, N, training, st, save=save)
+                up = plan.contract[i][1].forward(a, N, training, st, save=save)
+            prob = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
+            call("ocrs_det_outconv_fwd", up.p, up.ss, N, d[0], H, W, *up.xfp(), ptr(plan.out.weight),
+                 ptr(plan.out.bias), ptr(prob), st)
+        if save is not None:
+            ctx.recs = save
+            ctx.plan = plan
+            ctx.geom = (N, H, W, hs, ws)
+            ctx.acts = (xin, cat, catxf, pooled_src, dict(up_inputs), up, prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        plan: _Plan = ctx.plan
+        N, H, W, hs, ws = ctx.geom
+        xin, cat, catxf, pooled_src, up_inputs, last, prob = ctx.acts
+        d, L = plan.depth, plan.levels
+        dev = prob.device
+        lib = _lib.lib()
+        st = _lib.stream_ptr(dev)
+        dprob = dprob.contiguous().float()
+        grads: dict = {}
+        recs = ctx.recs
+
+        def put(tensors, gs):
+            for t, g in zip(tensors, gs):
+                grads[id(t)] = g
+
+        with torch.cuda.device(dev):
+            # out_conv + sigmoid
+            rows = lib.ocrs_det_outconv_bwd_rows(N, H, W)
+            part = torch.empty((rows, d[0] + 1), dtype=torch.float32, device=dev)
+            d_a = new_view(N, d[0], H, W, dev)
+            call("ocrs_det_outconv_bwd", ptr(dprob), ptr(prob), last.p, last.ss, N, d[0], H, W, *last.xfp(),
+                 ptr(plan.out.weight), d_a.p, d_a.ss, ptr(part), st)
+            wb = torch.empty((d[0] + 1,), dtype=torch.float32, device=dev)
+            _finalize(part, rows, d[0] + 1, wb, st)
+            put([plan.out.weight, plan.out.bias], [wb[: d[0]].reshape(1, d[0], 1, 1).clone(), wb[d[0] :].clone()])
+
+            dcat = [None] * L
+            # up path, in reverse of forward order: up[0] first
+            for i in range(L):
+                c = d[i]
+                gB, d_mid = plan.contract[i][1].backward(recs, d_a, N, st, None)
+                put(plan.contract[i][1].params(), gB)
+                dcat[i] = new_view(N, 2 * c, hs[i], ws[i], dev)
+                gA, _ = plan.contract[i][0].backward(recs, d_mid, N, st, dcat[i])
+                put(plan.contract[i][0].params(), gA)
+                # ConvTranspose2d
+                t = plan.upT[i]
+                up_in = up_inputs[i]
+                dlo = dcat[i].chan(0, c)
+                d_up = new_view(N, up_in.C, up_in.H, up_in.W, dev)
+                call("ocrs_det_convt_bwd_data", dlo.p, dlo.ss, N, c, hs[i], ws[i], ptr(t.weight), up_in.C, up_in.H,
+                     up_in.W, d_up.p, d_up.ss, st)
+                workers = lib.ocrs_det_convt_wgrad_workers(N, up_in.H, up_in.W)
+                wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
+                call("ocrs_det_convt_wgrad", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
+                     dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
+                dw = torch.empty_like(t.weight)
+                _finalize(wpart, workers, t.weight.numel(), dw, st)
+                brows = lib.ocrs_reduce_rows(N, hs[i] * ws[i])
+                bpart = torch.empty((brows, c), dtype=torch.float32, device=dev)
+                call("ocrs_plane_sum", dlo.p, dlo.ss, N, c, hs[i] * ws[i], ptr(bpart), st)
+                db = torch.empty_like(t.bias)
+                _finalize(bpart, brows, c, db, st)
+                put([t.weight, t.bias], [dw, db])
+                d_a = d_up  # gradient w.r.t. the activated input of this ConvT
+            # d_a now = gradient w.r.t. x_down[L-1] (pooled, activated)
+            d_pooled = d_a
+            for i in reversed(range(L)):
+                b = pooled_src[i]
+                d_full = new_view(N, b.C, b.H, b.W, dev)
+                call("ocrs_det_pool2_bwd", b.p, b.ss, N, b.C, b.H, b.W, *b.xfp(), d_pooled.p, d_pooled.ss,
+                     d_full.p, d_full.ss, st)
+                gB, d_mid = plan.down[i][1].backward(recs, d_full, N, st, None)
+                put(plan.down[i][1].params(), gB)
+                # input of down[i] is the skip half of cat[i]; its gradient already holds the Up-path part
+                dskip = dcat[i].chan(d[i], 2 * d[i])
+                gA, _ = plan.down[i][0].backward(recs, d_mid, N, st, dskip, accumulate=True)
+                put(plan.down[i][0].params(), gA)
+                d_pooled = dskip
+            # in_conv: d_pooled is now the gradient w.r.t. the activated in_conv output
+            gB, d_mid = plan.in_conv[1].backward(recs, d_pooled, N, st, None)
+            put(plan.in_conv[1].params(), gB)
+            gA, dx = plan.in_conv[0].backward(recs, d_mid, N, st, None)
+            put(plan.in_conv[0].params(), gA)
+        dxt = dx.t if ctx.needs_input_grad[1] else None
+        out = [None, dxt] + [grads.get(id(p)) for p in plan.all_params()]
+        ctx.acts = None
+        return tuple(out)
+
+
+def detection_forward(model, x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("ocrs_models_b200.DetectionModel has no CPU path: input must be a CUDA tensor")
+    if x.dim() != 4 or x.shape[1] != 1:
+        raise RuntimeError(f"expected (N, 1, H, W) input, got {tuple(x.shape)}")
+    plan = model.__dict__.get("_plan")
+    if plan is None:
+        plan = _Plan(model)
+        model.__dict__["_plan"] = plan
+    x = x.float().contiguous()
+    return _DetFunction.apply(plan, x, *plan.all_params())

@@ -115,3 +115,43 @@ class CTCLoss(nn.Module):
         return _CTCFunction.apply(
             log_probs, targets, input_lengths, target_lengths, self.blank, _REDUCTION[self.reduction], self.zero_infinity
         )
+
+
+class _BalancedBCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        if not pred.is_cuda:
+            raise RuntimeError("ocrs_models_b200.balanced_cross_entropy_loss has no CPU path")
+        if pred.shape != target.shape:
+            raise RuntimeError("pred and target must have the same shape")
+        dev = pred.device
+        p = pred.detach().float().contiguous()
+        t = target.detach().to(device=dev, dtype=torch.float32).contiguous()
+        n = p.numel()
+        lib = _lib.lib()
+        state = torch.zeros((lib.ocrs_bce_state_words(),), dtype=torch.int32, device=dev)
+        loss_map = torch.empty((n,), dtype=torch.float32, device=dev)
+        partials = torch.empty((lib.ocrs_bce_blocks(),), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("ocrs_balanced_bce_fwd", ptr(p), ptr(t), n, ptr(loss_map), ptr(state), ptr(partials), ptr(loss),
+                 _lib.stream_ptr(dev))
+        ctx.save_for_backward(p, t, loss_map, state)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, t, loss_map, state = ctx.saved_tensors
+        dev = p.device
+        go = grad_out.detach().float().contiguous()
+        dp = torch.empty_like(p)
+        with torch.cuda.device(dev):
+            call("ocrs_balanced_bce_bwd", ptr(p), ptr(t), ptr(loss_map), p.numel(), ptr(state), ptr(go), ptr(dp),
+                 _lib.stream_ptr(dev))
+        return dp, None
+
+
+def balanced_cross_entropy_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Balanced BCE between probability maps (reference train_detection.py:225-263), fully on
+    device: no host sync for the positive/negative counts, radix-select instead of two topk."""
+    return _BalancedBCEFunction.apply(pred, target)

@@ -1,0 +1,296 @@
+"""Detection kernels through the C-ABI vs the oracle (oracle/functional.py, CPU, fp64 = ground truth)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+from oracle import functional as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    from ocrs_models_b200 import _lib
+
+    return _lib.stream_ptr(torch.device("cuda:0"))
+
+
+def _rand_xf(C, g):
+    sc = torch.randn(C, generator=g) * 0.5 + 1.0
+    sc[::3] *= -1  # negative BN scales occur in trained models
+    sh = torch.randn(C, generator=g) * 0.3
+    lo = torch.zeros(C)
+    return sc, sh, lo
+
+
+def _apply_xf(x, xf):
+    sc, sh, lo = xf
+    return torch.maximum(x * sc[None, :, None, None] + sh[None, :, None, None], lo[None, :, None, None])
+
+
+@pytest.mark.parametrize("N,cin,cout,H,W,with_xf", [(2, 1, 8, 37, 45, False), (2, 8, 16, 64, 64, True), (1, 16, 16, 33, 70, True), (2, 64, 32, 9, 12, True), (1, 128, 256, 5, 3, True), (1, 24, 40, 17, 19, True)])
+def test_separable_block_fwd_bwd(N, cin, cout, H, W, with_xf):
+    from ocrs_models_b200.det_engine import View, _Sep, new_view
+    from ocrs_models_b200.models import _separable
+
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    torch.manual_seed(cin * 100 + cout)
+    mod = _separable(cin, cout)
+    with torch.no_grad():
+        mod.seq[2].weight.copy_(torch.randn(cout, generator=g) * 0.5 + 1)
+        mod.seq[2].bias.copy_(torch.randn(cout, generator=g) * 0.2)
+    x = torch.randn(N, cin, H, W, generator=g)
+    xf = _rand_xf(cin, g) if with_xf else None
+    d_a = torch.randn(N, cout, H, W, generator=g)
+
+    # oracle in fp64
+    sd = {"b." + k: v.detach().double().clone() for k, v in mod.state_dict().items()}
+    for k in ("b.seq.0.weight", "b.seq.1.weight", "b.seq.2.weight", "b.seq.2.bias"):
+        sd[k].requires_grad_(True)
+    xa = (_apply_xf(x, xf) if xf else x).double().requires_grad_(True)
+    nb = {}
+    out = O._depthwise_block(sd, "b", xa, True, nb)
+    out.backward(d_a.double())
+
+    modc = _separable(cin, cout).cuda()
+    modc.load_state_dict(mod.state_dict())
+    blk = _Sep(modc)
+    xd = x.cuda()
+    xfd = tuple(a.cuda() for a in xf) if xf else None
+    inp = View(xd, 0, cin * H * W, cin, H, W, xfd)
+    recs = {}
+    y = blk.forward(inp, N, True, _stream(), save=recs)
+    act = _apply_xf(y.t, y.xf)
+    assert rel_l2(act, out) < 1e-5
+    assert rel_l2(modc.seq[2].running_mean, nb["b.seq.2.running_mean"]) < 1e-5
+    assert rel_l2(modc.seq[2].running_var, nb["b.seq.2.running_var"]) < 1e-5
+    assert int(modc.seq[2].num_batches_tracked) == 1
+    dad = d_a.cuda()
+    grads, dx = blk.backward(recs, View(dad, 0, cout * H * W, cout, H, W), N, _stream(), None)
+    torch.cuda.synchronize()
+    assert rel_l2(dx.t, xa.grad) < 2e-4, "dx"
+    names = ["b.seq.0.weight", "b.seq.1.weight", "b.seq.2.weight", "b.seq.2.bias"]
+    for gname, got in zip(names, grads):
+        want = sd[gname].grad
+        err = (got.cpu().double() - want).norm() / max(want.norm(), 1e-3 * d_a.numel() ** 0.5)
+        assert err < 1e-3, (gname, float(err))
+
+
+def test_dw_bwd_accumulate_into_strided_view():
+    from ocrs_models_b200._lib import call, ptr
+
+    g = torch.Generator().manual_seed(1)
+    N, C, H, W = 2, 8, 21, 34
+    gr = torch.randn(N, C, H, W, generator=g).cuda()
+    w = torch.randn(C, 1, 3, 3, generator=g).cuda()
+    base = torch.randn(N, 2 * C, H, W, generator=g).cuda()
+    ref = base.clone()
+    ref[:, C:] += F.conv_transpose2d(gr, w, padding=1, groups=C)
+    dst_off = C * H * W
+    call("ocrs_det_dw_bwd", ptr(gr), C * H * W, ptr(gr), C * H * W, N, C, H, W, None, None, None, ptr(w),
+         base.data_ptr() + 4 * dst_off, 2 * C * H * W, 1, None, _stream())
+    assert rel_l2(base, ref) < 1e-6
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 51), (2, 3)])
+def test_pool_fwd_bwd(H, W):
+    from ocrs_models_b200._lib import call, ptr
+
+    g = torch.Generator().manual_seed(H)
+    N, C = 2, 5
+    x = torch.randn(N, C, H, W, generator=g)
+    xf = _rand_xf(C, g)
+    a = _apply_xf(x, xf).requires_grad_(True)
+    ref = F.max_pool2d(a, 2)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+    xd, xfd = x.cuda(), [t.cuda() for t in xf]
+    Ho, Wo = H // 2, W // 2
+    out = torch.empty(N, C, Ho, Wo, device="cuda")
+    call("ocrs_det_pool2_fwd", ptr(xd), C * H * W, N, C, H, W, *[ptr(t) for t in xfd], ptr(out), C * Ho * Wo, _stream())
+    assert rel_l2(out, ref) < 1e-6  # fmaf vs mul+add in the test's own transform
+    din = torch.full((N, C, H, W), 7.0, device="cuda")
+    doutd = dout.cuda()
+    call("ocrs_det_pool2_bwd", ptr(xd), C * H * W, N, C, H, W, *[ptr(t) for t in xfd], ptr(doutd), C * Ho * Wo,
+         ptr(din), C * H * W, _stream())
+    assert rel_l2(din, a.grad) < 1e-6
+
+
+@pytest.mark.parametrize("N,cin,cout,h,w,Hs,Ws", [(2, 16, 8, 20, 24, 40, 48), (1, 256, 128, 3, 2, 7, 5), (2, 32, 16, 9, 7, 18, 15), (1, 24, 12, 5, 6, 11, 13)])
+def test_convt_fwd_bwd(N, cin, cout, h, w, Hs, Ws):
+    from ocrs_models_b200._lib import call, lib, ptr
+
+    g = torch.Generator().manual_seed(cin + h)
+    x = torch.randn(N, cin, h, w, generator=g)
+    xf = _rand_xf(cin, g)
+    wt = (torch.randn(cin, cout, 3, 3, generator=g) * 0.1).double().requires_grad_(True)
+    b = torch.randn(cout, generator=g).double().requires_grad_(True)
+    a = _apply_xf(x, xf).double().requires_grad_(True)
+    ref = F.conv_transpose2d(a, wt, b, stride=2)[:, :, :Hs, :Ws]
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout.double())
+    xd, xfd = x.cuda(), [ptr(t.cuda()) for t in xf]
+    keep = [t.cuda() for t in xf]
+    xfd = [ptr(t) for t in keep]
+    wd, bd = wt.detach().float().cuda(), b.detach().float().cuda()
+    # write into the lower half of a wider concat buffer
+    cat = torch.zeros(N, cout + 3, Hs, Ws, device="cuda")
+    call("ocrs_det_convt_fwd", ptr(xd), cin * h * w, N, cin, h, w, *xfd, ptr(wd), ptr(bd), cout, ptr(cat),
+         (cout + 3) * Hs * Ws, Hs, Ws, _stream())
+    assert rel_l2(cat[:, :cout], ref) < 1e-5
+    assert cat[:, cout:].abs().max().item() == 0
+    dcat = torch.zeros_like(cat)
+    dcat[:, :cout] = dout.cuda()
+    dx = torch.empty(N, cin, h, w, device="cuda")
+    call("ocrs_det_convt_bwd_data", ptr(dcat), (cout + 3) * Hs * Ws, N, cout, Hs, Ws, ptr(wd), cin, h, w, ptr(dx),
+         cin * h * w, _stream())
+    assert rel_l2(dx, a.grad) < 1e-5
+    workers = lib().ocrs_det_convt_wgrad_workers(N, h, w)
+    part = torch.empty(workers, cin, cout, 3, 3, device="cuda")
+    call("ocrs_det_convt_wgrad", ptr(xd), cin * h * w, N, cin, h, w, *xfd, ptr(dcat), (cout + 3) * Hs * Ws, cout, Hs,
+         Ws, ptr(part), _stream())
+    dw = torch.empty(cin, cout, 3, 3, device="cuda")
+    call("ocrs_finalize_partials", ptr(part), workers, dw.numel(), ptr(dw), _stream())
+    assert rel_l2(dw, wt.grad) < 1e-5
+    rows = lib().ocrs_reduce_rows(N, Hs * Ws)
+    bp = torch.empty(rows, cout, device="cuda")
+    call("ocrs_plane_sum", ptr(dcat), (cout + 3) * Hs * Ws, N, cout, Hs * Ws, ptr(bp), _stream())
+    db = torch.empty(cout, device="cuda")
+    call("ocrs_finalize_partials", ptr(bp), rows, cout, ptr(db), _stream())
+    assert rel_l2(db, b.grad) < 1e-5
+
+
+def _loss_case(p, t):
+    from ocrs_models_b200 import balanced_cross_entropy_loss
+
+    pd = p.cuda().requires_grad_(True)
+    lo = balanced_cross_entropy_loss(pd, t.cuda())
+    lo.backward()
+    pc = p.double().requires_grad_(True)
+    lr = O.balanced_cross_entropy_loss(pc, t.double())
+    lr.backward()
+    return lo.detach().cpu(), pd.grad.cpu(), lr.detach(), pc.grad
+
+
+@pytest.mark.parametrize("shape,frac", [((2, 1, 64, 80), 0.1), ((1, 1, 301, 257), 0.7), ((3, 1, 33, 33), 0.5)])
+def test_balanced_bce_vs_oracle(shape, frac):
+    g = torch.Generator().manual_seed(int(frac * 100))
+    p = torch.sigmoid(torch.randn(shape, generator=g) * 3)
+    t = (torch.rand(shape, generator=g) < frac).float()
+    t.view(-1)[5] = 1.2   # out-of-range targets are clamped (train_detection.py:249)
+    t.view(-1)[9] = -0.1
+    t.view(-1)[11] = 0.5  # in neither class
+    lo, go, lr, gr = _loss_case(p, t)
+    assert abs(lo - lr) < 1e-5 * abs(lr)
+    assert rel_l2(go, gr) < 1e-5
+
+
+def test_balanced_bce_saturated_and_ties():
+    g = torch.Generator().manual_seed(4)
+    shape = (1, 1, 40, 40)
+    p = torch.sigmoid(torch.randn(shape, generator=g))
+    t = (torch.rand(shape, generator=g) < 0.2).float()
+    p.view(-1)[:7] = 0.0  # log clamp at -100
+    p.view(-1)[7:12] = 1.0
+    t.view(-1)[:12] = torch.tensor([1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 1, 0]).float()
+    lo, go, lr, gr = _loss_case(p, t)
+    assert abs(lo - lr) < 1e-5 * abs(lr)
+    # tie at the threshold: quantised losses -> many equal values; loss must still agree
+    p2 = (torch.randint(1, 8, shape, generator=g).float() / 8.0)
+    lo, go, lr, gr = _loss_case(p2, t)
+    assert abs(lo - lr) < 1e-5 * abs(lr)
+    assert abs(go.sum() - gr.sum()) < 1e-4 * gr.abs().sum()
+
+
+def test_balanced_bce_degenerate_no_positives():
+    from ocrs_models_b200 import balanced_cross_entropy_loss
+
+    p = torch.full((1, 1, 8, 8), 0.3, device="cuda", requires_grad=True)
+    lo = balanced_cross_entropy_loss(p, torch.zeros(1, 1, 8, 8, device="cuda"))
+    lo.backward()
+    assert torch.isnan(lo)  # mean of an empty selection, as in the reference
+    assert p.grad.abs().max().item() == 0
+
+
+def _det_models(seed=1234):
+    from ocrs_models_b200 import DetectionModel
+
+    torch.manual_seed(seed)
+    m = DetectionModel()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():  # move BN affine away from (1, 0) so its gradients are exercised
+        for k, v in m.named_parameters():
+            if ".seq.2." in k:
+                v.add_(torch.randn(v.shape, generator=g) * 0.2)
+    return m
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 96, 80), (1, 200, 152), (2, 64, 64)])
+def test_full_model_train_step_vs_oracle(N, H, W):
+    from ocrs_models_b200 import balanced_cross_entropy_loss
+
+    m = _det_models()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(N, 1, H, W, generator=g) - 0.5
+    mask = (torch.rand(N, 1, H, W, generator=g) < 0.1).float()
+    batch = {"image": x, "mask": mask}
+    out64, loss64, g64, nb64 = O.train_step_grads("det", sd, batch, torch.float64)
+    out32, loss32, g32, _ = O.train_step_grads("det", sd, batch, torch.float32)
+
+    m = m.cuda().train()
+    y = m(x.cuda())
+    loss = balanced_cross_entropy_loss(y, mask.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_l2(y, out64) < 1e-4, "probabilities"
+    assert abs(loss.item() - loss64.item()) < 1e-4 * abs(loss64.item())
+    ours = {k: p.grad for k, p in m.named_parameters()}
+    gn = torch.sqrt(sum((v.double() ** 2).sum() for v in g64.values()))
+    err = torch.sqrt(sum(((ours[k].cpu().double() - g64[k]) ** 2).sum() for k in g64)) / gn
+    err32 = torch.sqrt(sum(((g32[k].double() - g64[k]) ** 2).sum() for k in g64)) / gn
+    print(f"global grad rel-L2: ours {err:.3e}  fp32-oracle {err32:.3e}")
+    assert err < 1e-3
+    floor = gn / len(g64) ** 0.5
+    for k in g64:
+        e = (ours[k].cpu().double() - g64[k]).norm()
+        e32 = (g32[k].double() - g64[k]).norm()
+        assert e <= max(1e-3 * g64[k].norm(), 1e-3 * floor, 10 * e32), (k, float(e), float(g64[k].norm()), float(e32))
+    for k, v in nb64.items():
+        if v.is_floating_point():
+            assert rel_l2(m.state_dict()[k], v) < 1e-4, k
+        else:
+            assert int(m.state_dict()[k]) == int(v)
+
+
+def test_full_model_golden_and_eval_mode(golden):
+    from ocrs_models_b200 import DetectionModel, balanced_cross_entropy_loss
+
+    gold = golden("det_96x80")
+    torch.manual_seed(1234)
+    m = DetectionModel().cuda().train()
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 1, 96, 80, generator=g) - 0.5
+    mask = (torch.rand(2, 1, 96, 80, generator=g) < 0.1).float()
+    y = m(x.cuda())
+    loss = balanced_cross_entropy_loss(y, mask.cuda())
+    loss.backward()
+    np.testing.assert_allclose(y.detach().cpu().numpy(), gold["y"], rtol=1e-3, atol=1e-5)
+    assert abs(loss.item() - gold["loss"]) < 1e-4 * gold["loss"]
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters())).item()
+    assert abs(gn - gold["grad_norm"]) < 1e-3 * gold["grad_norm"]
+    # eval mode uses the running statistics and records nothing for backward
+    m.eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.inference_mode():
+        ye = m(x.cuda())
+    ref = O.det_forward(sd, x, training=False)
+    assert rel_l2(ye, ref) < 1e-4
+
+
+def test_rejects_cpu_input():
+    from ocrs_models_b200 import DetectionModel
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DetectionModel()(torch.zeros(1, 1, 64, 64))
