@@ -47,6 +47,27 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_convt_wgrad_workers": [I, I, I],
     "ocrs_det_convt_wgrad": [P, L, I, I, I, I, P, P, P, P, L, I, I, I, P, P],
     "ocrs_plane_sum": [P, L, I, I, L, P, P],
+    # GEMM / im2col (csrc/gemm.cu)
+    "ocrs_gemm_stat_rows": [I],
+    "ocrs_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
+    "ocrs_gemm_splits": [I, I],
+    "ocrs_im2col_nhwc": [P, I, I, I, I, I, I, I, I, I, I, P, P],
+    "ocrs_colsum_rows": [I],
+    "ocrs_colsum": [P, L, I, I, P, P],
+    # recognition (csrc/rec.cu)
+    "ocrs_rec_conv0_fwd": [P, I, I, I, P, P, P, P],
+    "ocrs_rec_conv0_bwd_blocks": [],
+    "ocrs_rec_conv0_bwd": [P, I, I, I, P, P, P, P, P],
+    "ocrs_rec_bn_act_pool_fwd": [P, I, I, I, I, I, I, I, I, P, P, P, L, L, L, P],
+    "ocrs_rec_pool_bwd_blocks": [],
+    "ocrs_rec_bn_act_pool_bwd_reduce": [P, I, I, I, I, I, I, I, I, P, P, P, P, P, L, L, L, P, P],
+    "ocrs_rec_bn_act_pool_bwd_apply": [P, I, I, I, I, I, I, I, I, P, P, P, P, P, P, L, L, L, P, P],
+    "ocrs_relu_bwd": [P, P, L, P],
+    "ocrs_gru_layer_fwd": [P, P, P, P, P, P, P, P, I, I, P],
+    "ocrs_gru_layer_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
+    "ocrs_log_softmax_fwd": [P, P, I, I, P],
+    "ocrs_log_softmax_bwd": [P, P, P, I, I, P],
+    "ocrs_transpose": [P, P, I, I, P],
     # balanced BCE (csrc/det_loss.cu)
     "ocrs_bce_state_words": [],
     "ocrs_bce_blocks": [],

@@ -18,8 +18,11 @@ void ocrs_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
-#define OCRS_CHECK_LAUNCH(name)                                              \
+void ocrs_count_launches(int n);
+#define OCRS_CHECK_LAUNCH(name) OCRS_CHECK_LAUNCH_N(name, 1)
+#define OCRS_CHECK_LAUNCH_N(name, n)                                         \
   do {                                                                       \
+    ocrs_count_launches(n);                                                  \
     cudaError_t e__ = cudaGetLastError();                                    \
     if (e__ != cudaSuccess) {                                                \
       ocrs_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

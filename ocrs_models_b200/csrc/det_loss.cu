@@ -184,7 +184,7 @@ int ocrs_balanced_bce_fwd(const float* pred, const float* target, long long n, f
   }
   bce_sum_kernel<<<nb, 256, 0, s>>>(loss_map, n, state, partials);
   bce_loss_finalize_kernel<<<1, 256, 0, s>>>(partials, nb, state, loss);
-  OCRS_CHECK_LAUNCH("balanced_bce_fwd");
+  OCRS_CHECK_LAUNCH_N("balanced_bce_fwd", 10);
   return 0;
 }
 

@@ -1,0 +1,609 @@
+// Recognition (CRNN) kernels that are not plain GEMMs (reference ocrs_models/models.py:179-268).
+//
+// Activations of the conv stack are NHWC fp32. conv.0 (Cin = 1) is a direct convolution fused
+// with ReLU + MaxPool2 (models.py:180-187); every other convolution is im2col + GEMM (gemm.cu)
+// followed by one fused BatchNorm-affine / ReLU / pool kernel here. The GRU recurrence
+// (models.py:245, gate equations torch/nn/modules/rnn.py) runs one launch per time step for both
+// directions; LogSoftmax (models.py:250) is one warp per row.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// conv.0: Conv2d(1, 32, 3, pad 1) + bias -> ReLU -> MaxPool2d(2). Thread = pooled pixel x 8 channels.
+__device__ __forceinline__ void conv0_patch(const float* __restrict__ x, int H, int W, int n, int py,
+                                            int px, float (&p)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int iy = 2 * py - 1 + r, ix = 2 * px - 1 + c;
+      p[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[((size_t)n * H + iy) * W + ix] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+conv0_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
+                 const float* __restrict__ bias, float* __restrict__ out) {
+  __shared__ __align__(16) float sw[9 * 32];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 288; i += 256) sw[(i % 9) * 32 + i / 9] = w[i];  // [tap][c]
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Hp = H / 2, Wp = W / 2;
+  const long long total = (long long)N * Hp * Wp * 4;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i & 3);
+  long long r = i >> 2;
+  const int px = (int)(r % Wp);
+  r /= Wp;
+  const int py = (int)(r % Hp), n = (int)(r / Hp);
+  float p[4][4];
+  conv0_patch(x, H, W, n, py, px, p);
+  float best[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) best[c] = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int dy = q >> 1, dx = q & 1;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = sb[cg * 8 + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float xv = p[dy + k / 3][dx + k % 3];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = fmaf(xv, sw[k * 32 + cg * 8 + c], v[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], v[c]);
+  }
+  float4* o = reinterpret_cast<float4*>(out + ((((size_t)n * Hp + py) * Wp + px) * 32 + cg * 8));
+  o[0] = make_float4(fmaxf(best[0], 0.f), fmaxf(best[1], 0.f), fmaxf(best[2], 0.f), fmaxf(best[3], 0.f));
+  o[1] = make_float4(fmaxf(best[4], 0.f), fmaxf(best[5], 0.f), fmaxf(best[6], 0.f), fmaxf(best[7], 0.f));
+}
+
+// Weight/bias gradient of conv.0 (its input is the image: no data gradient). Recomputes the four
+// pre-pool values to route d_out to the first maximum (aten tie rule) when it is positive.
+// partials: [gridDim.x][32][10] (9 taps + bias).
+__global__ void __launch_bounds__(256)
+conv0_bwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
+                 const float* __restrict__ bias, const float* __restrict__ dout,
+                 float* __restrict__ partials) {
+  __shared__ __align__(16) float sw[9 * 32];
+  __shared__ float sb[32];
+  __shared__ float red[8][4][80];
+  for (int i = threadIdx.x; i < 288; i += 256) sw[(i % 9) * 32 + i / 9] = w[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Hp = H / 2, Wp = W / 2;
+  const long long total = (long long)N * Hp * Wp * 4;
+  const int cg = threadIdx.x & 3;
+  float acc[8][10];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[c][k] = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    long long r = i >> 2;
+    const int px = (int)(r % Wp);
+    r /= Wp;
+    const int py = (int)(r % Hp), n = (int)(r / Hp);
+    float p[4][4];
+    conv0_patch(x, H, W, n, py, px, p);
+    const float4* gp = reinterpret_cast<const float4*>(dout + ((((size_t)n * Hp + py) * Wp + px) * 32 + cg * 8));
+    const float4 g0 = gp[0], g1 = gp[1];
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float v[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int dy = q >> 1, dx = q & 1;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[q][c] = sb[cg * 8 + c];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float xv = p[dy + k / 3][dx + k % 3];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[q][c] = fmaf(xv, sw[k * 32 + cg * 8 + c], v[q][c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      int am = 0;
+      float m = v[0][c];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][c] > m) { m = v[q][c]; am = q; }
+      const float gv = m > 0.f ? g[c] : 0.f;
+      acc[c][9] += gv;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float gq = (q == am) ? gv : 0.f;
+        const int dy = q >> 1, dx = q & 1;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[c][k] = fmaf(gq, p[dy + k / 3][dx + k % 3], acc[c][k]);
+      }
+    }
+  }
+  // reduce over lanes with the same channel group (lane & 3), then over warps
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      float s = acc[c][k];
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if (lane < 4) red[wid][lane][c * 10 + k] = s;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 320; i += 256) {
+    const int g4 = i / 80, e = i - g4 * 80;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][g4][e];
+    partials[(size_t)blockIdx.x * 320 + (g4 * 8 + e / 10) * 10 + e % 10] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm affine (+ReLU) + pooling over NHWC. mode 0 = max, 1 = avg. Pool window (ph, pw),
+// floor semantics; out element (n, oy, ox, c) at out[n*son + oy*soh + ox*sow + c].
+struct PoolGeom {
+  int N, H, W, C, ph, pw, Hp, Wp, mode, relu;
+  long long son, soh, sow;
+};
+
+__device__ __forceinline__ float bn_act(float v, float s, float t, int relu) {
+  v = fmaf(v, s, t);
+  return relu ? fmaxf(v, 0.f) : v;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_pool_fwd_kernel(const float* __restrict__ y, PoolGeom g, const float* __restrict__ sc,
+                       const float* __restrict__ sh, float* __restrict__ out) {
+  const int C4 = g.C >> 2;
+  const long long total = (long long)g.N * g.Hp * g.Wp * C4;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  long long r = i / C4;
+  const int ox = (int)(r % g.Wp);
+  r /= g.Wp;
+  const int oy = (int)(r % g.Hp), n = (int)(r / g.Hp);
+  const float4 s = reinterpret_cast<const float4*>(sc)[c4], t = reinterpret_cast<const float4*>(sh)[c4];
+  float4 res = g.mode == 0 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int dy = 0; dy < g.ph; ++dy)
+    for (int dx = 0; dx < g.pw; ++dx) {
+      const float4 v = *reinterpret_cast<const float4*>(
+          y + (((size_t)n * g.H + oy * g.ph + dy) * g.W + ox * g.pw + dx) * g.C + c4 * 4);
+      const float a0 = bn_act(v.x, s.x, t.x, g.relu), a1 = bn_act(v.y, s.y, t.y, g.relu);
+      const float a2 = bn_act(v.z, s.z, t.z, g.relu), a3 = bn_act(v.w, s.w, t.w, g.relu);
+      if (g.mode == 0) {
+        res.x = fmaxf(res.x, a0); res.y = fmaxf(res.y, a1); res.z = fmaxf(res.z, a2); res.w = fmaxf(res.w, a3);
+      } else {
+        res.x += a0; res.y += a1; res.z += a2; res.w += a3;
+      }
+    }
+  if (g.mode == 1) {
+    const float inv = 1.f / (float)(g.ph * g.pw);
+    res.x *= inv; res.y *= inv; res.z *= inv; res.w *= inv;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)n * g.son + (size_t)oy * g.soh + (size_t)ox * g.sow + c4 * 4) = res;
+}
+
+// Routed gradient of one pooling window for one channel: returns dz at window position q.
+// For max: the first maximum takes g (if it passed the ReLU); avg: every position takes g / count.
+__device__ __forceinline__ void window_route(const float* v, int cnt, float s, float t, int relu, int mode,
+                                             float g, float* dz) {
+  if (mode == 1) {
+    const float q = g / (float)cnt;
+    for (int i = 0; i < cnt; ++i) dz[i] = q;
+    return;
+  }
+  int am = 0;
+  float m = bn_act(v[0], s, t, relu);
+  for (int i = 1; i < cnt; ++i) {
+    const float a = bn_act(v[i], s, t, relu);
+    if (a > m) { m = a; am = i; }
+  }
+  const bool pass = relu ? (fmaf(v[am], s, t) > 0.f) : true;
+  for (int i = 0; i < cnt; ++i) dz[i] = (i == am && pass) ? g : 0.f;
+}
+
+constexpr int MAXWIN = 8;
+// partials [gridDim.x][2][C]: sum dz, sum dz * yhat.
+__global__ void __launch_bounds__(256)
+bn_act_pool_bwd_reduce_kernel(const float* __restrict__ y, PoolGeom g, const float* __restrict__ sc,
+                              const float* __restrict__ sh, const float* __restrict__ mean,
+                              const float* __restrict__ invstd, const float* __restrict__ dout,
+                              float* __restrict__ partials) {
+  extern __shared__ float red[];  // [256/C4][2][C]
+  const int C4 = g.C >> 2, lanes = 256 / C4;
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const long long npix = (long long)g.N * g.Hp * g.Wp;
+  const int cnt = g.ph * g.pw;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  float s[4], t[4], mu[4], is[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s[j] = sc[c4 * 4 + j]; t[j] = sh[c4 * 4 + j]; mu[j] = mean[c4 * 4 + j]; is[j] = invstd[c4 * 4 + j]; }
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+    long long r = p;
+    const int ox = (int)(r % g.Wp);
+    r /= g.Wp;
+    const int oy = (int)(r % g.Hp), n = (int)(r / g.Hp);
+    const float4 gv = *reinterpret_cast<const float4*>(dout + (size_t)n * g.son + (size_t)oy * g.soh + (size_t)ox * g.sow + c4 * 4);
+    const float gj[4] = {gv.x, gv.y, gv.z, gv.w};
+    float v[4][MAXWIN];
+    for (int dy = 0; dy < g.ph; ++dy)
+      for (int dx = 0; dx < g.pw; ++dx) {
+        const float4 q = *reinterpret_cast<const float4*>(
+            y + (((size_t)n * g.H + oy * g.ph + dy) * g.W + ox * g.pw + dx) * g.C + c4 * 4);
+        const int wi = dy * g.pw + dx;
+        v[0][wi] = q.x; v[1][wi] = q.y; v[2][wi] = q.z; v[3][wi] = q.w;
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float dz[MAXWIN];
+      window_route(v[j], cnt, s[j], t[j], g.relu, g.mode, gj[j], dz);
+      for (int wi = 0; wi < cnt; ++wi) {
+        a[j] += dz[wi];
+        b[j] = fmaf(dz[wi], (v[j][wi] - mu[j]) * is[j], b[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[(pl * 2) * g.C + c4 * 4 + j] = a[j];
+    red[(pl * 2 + 1) * g.C + c4 * 4 + j] = b[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.C; i += 256) {
+    float sum = 0.f;
+    for (int q = 0; q < lanes; ++q) sum += red[q * 2 * g.C + i];
+    partials[(size_t)blockIdx.x * 2 * g.C + i] = sum;
+  }
+}
+
+// dy[n,h,w,c] = k1*dz + k2*y + k3 for every input position (positions outside any pooling window
+// have dz = 0 but still receive the batch-statistics terms).
+__global__ void __launch_bounds__(256)
+bn_act_pool_bwd_apply_kernel(const float* __restrict__ y, PoolGeom g, const float* __restrict__ sc,
+                             const float* __restrict__ sh, const float* __restrict__ k1,
+                             const float* __restrict__ k2, const float* __restrict__ k3,
+                             const float* __restrict__ dout, float* __restrict__ dy) {
+  const int C4 = g.C >> 2;
+  const long long total = (long long)g.N * g.H * g.W * C4;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  long long r = i / C4;
+  const int ix = (int)(r % g.W);
+  r /= g.W;
+  const int iy = (int)(r % g.H), n = (int)(r / g.H);
+  const int oy = iy / g.ph, ox = ix / g.pw;
+  const int me = (iy - oy * g.ph) * g.pw + (ix - ox * g.pw);
+  const bool inside = oy < g.Hp && ox < g.Wp;
+  const int cnt = g.ph * g.pw;
+  const float4 yv = *reinterpret_cast<const float4*>(y + (((size_t)n * g.H + iy) * g.W + ix) * g.C + c4 * 4);
+  const float ymine[4] = {yv.x, yv.y, yv.z, yv.w};
+  float dzv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (inside) {
+    const float4 gv = *reinterpret_cast<const float4*>(dout + (size_t)n * g.son + (size_t)oy * g.soh + (size_t)ox * g.sow + c4 * 4);
+    const float gj[4] = {gv.x, gv.y, gv.z, gv.w};
+    float v[4][MAXWIN];
+    for (int dy_ = 0; dy_ < g.ph; ++dy_)
+      for (int dx = 0; dx < g.pw; ++dx) {
+        const float4 q = *reinterpret_cast<const float4*>(
+            y + (((size_t)n * g.H + oy * g.ph + dy_) * g.W + ox * g.pw + dx) * g.C + c4 * 4);
+        const int wi = dy_ * g.pw + dx;
+        v[0][wi] = q.x; v[1][wi] = q.y; v[2][wi] = q.z; v[3][wi] = q.w;
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float dz[MAXWIN];
+      window_route(v[j], cnt, sc[c4 * 4 + j], sh[c4 * 4 + j], g.relu, g.mode, gj[j], dz);
+      float pick = 0.f;
+      for (int wi = 0; wi < cnt; ++wi) pick = (wi == me) ? dz[wi] : pick;
+      dzv[j] = pick;
+    }
+  }
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = fmaf(k1[c4 * 4 + j], dzv[j], fmaf(k2[c4 * 4 + j], ymine[j], k3[c4 * 4 + j]));
+  *reinterpret_cast<float4*>(dy + (((size_t)n * g.H + iy) * g.W + ix) * g.C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ReLU backward in place on a GEMM output that was stored post-ReLU: d *= (a > 0).
+__global__ void relu_bwd_kernel(const float* __restrict__ a, float* __restrict__ d, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 av = reinterpret_cast<const float4*>(a)[i];
+  float4 dv = reinterpret_cast<float4*>(d)[i];
+  dv.x = av.x > 0.f ? dv.x : 0.f; dv.y = av.y > 0.f ? dv.y : 0.f;
+  dv.z = av.z > 0.f ? dv.z : 0.f; dv.w = av.w > 0.f ? dv.w : 0.f;
+  reinterpret_cast<float4*>(d)[i] = dv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GRU (nn.GRU gate order r, z, n; hidden 256; both directions in one launch via blockIdx.y).
+constexpr int GH = 256;
+struct GruDirs {
+  const float* gi[2];    // [T*N][768] input projections (incl. b_ih)
+  const float* whh[2];   // fwd: [768][256]; bwd step: transposed [256][768]
+  const float* bhh[2];   // [768]
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// One time step. out: [T][N][512] (dir d in columns d*256..); gates: [T][N][2][4][256] (r,z,n,gh_n).
+// Thread = (2 batch rows, 1 hidden unit); block = 32 row-pairs x 4 units.
+__global__ void __launch_bounds__(128)
+gru_step_fwd_kernel(GruDirs p, float* __restrict__ out, float* __restrict__ gates, int T, int N, int step) {
+  const int d = blockIdx.y;
+  const int t = d == 0 ? step : T - 1 - step;
+  const int tp = d == 0 ? t - 1 : t + 1;
+  const int j = blockIdx.x * 4 + (threadIdx.x & 3);
+  const int n0 = (blockIdx.z * 32 + (threadIdx.x >> 2)) * 2;
+  if (n0 >= N) return;
+  const bool two = n0 + 1 < N;
+  const int n1 = two ? n0 + 1 : n0;
+  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  const float* w = p.whh[d];
+  float hp0 = 0.f, hp1 = 0.f;
+  if (step > 0) {
+    const float* h0 = out + ((size_t)tp * N + n0) * 512 + d * GH;
+    const float* h1 = out + ((size_t)tp * N + n1) * 512 + d * GH;
+    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)j * GH);
+    const float4* wz = reinterpret_cast<const float4*>(w + (size_t)(GH + j) * GH);
+    const float4* wn = reinterpret_cast<const float4*>(w + (size_t)(2 * GH + j) * GH);
+#pragma unroll 4
+    for (int k4 = 0; k4 < GH / 4; ++k4) {
+      const float4 a = reinterpret_cast<const float4*>(h0)[k4], b = reinterpret_cast<const float4*>(h1)[k4];
+      const float4 r4 = __ldg(wr + k4), z4 = __ldg(wz + k4), q4 = __ldg(wn + k4);
+      acc[0][0] = fmaf(a.x, r4.x, fmaf(a.y, r4.y, fmaf(a.z, r4.z, fmaf(a.w, r4.w, acc[0][0]))));
+      acc[0][1] = fmaf(a.x, z4.x, fmaf(a.y, z4.y, fmaf(a.z, z4.z, fmaf(a.w, z4.w, acc[0][1]))));
+      acc[0][2] = fmaf(a.x, q4.x, fmaf(a.y, q4.y, fmaf(a.z, q4.z, fmaf(a.w, q4.w, acc[0][2]))));
+      acc[1][0] = fmaf(b.x, r4.x, fmaf(b.y, r4.y, fmaf(b.z, r4.z, fmaf(b.w, r4.w, acc[1][0]))));
+      acc[1][1] = fmaf(b.x, z4.x, fmaf(b.y, z4.y, fmaf(b.z, z4.z, fmaf(b.w, z4.w, acc[1][1]))));
+      acc[1][2] = fmaf(b.x, q4.x, fmaf(b.y, q4.y, fmaf(b.z, q4.z, fmaf(b.w, q4.w, acc[1][2]))));
+    }
+    hp0 = h0[j];
+    hp1 = h1[j];
+  }
+  const float br = p.bhh[d][j], bz = p.bhh[d][GH + j], bn = p.bhh[d][2 * GH + j];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (q == 1 && !two) break;
+    const int n = q == 0 ? n0 : n1;
+    const float* gi = p.gi[d] + ((size_t)t * N + n) * 768;
+    const float r = sigmoidf_(gi[j] + acc[q][0] + br);
+    const float z = sigmoidf_(gi[GH + j] + acc[q][1] + bz);
+    const float ghn = acc[q][2] + bn;
+    const float nn = tanhf(gi[2 * GH + j] + r * ghn);
+    const float hp = q == 0 ? hp0 : hp1;
+    const float h = (1.f - z) * nn + z * hp;
+    out[((size_t)t * N + n) * 512 + d * GH + j] = h;
+    float* gs = gates + (((size_t)t * N + n) * 2 + d) * 4 * GH;
+    gs[j] = r; gs[GH + j] = z; gs[2 * GH + j] = nn; gs[3 * GH + j] = ghn;
+  }
+}
+
+// One BPTT step. dout: [T][N][512]; dgi/dgh: per direction [T*N][768]; carry: [2][N][256] holds
+// dh(t_next) * z(t_next). whh here is the TRANSPOSED recurrent weight [256][768].
+struct GruBwd {
+  const float* whhT[2];
+  float* dgi[2];
+  float* dgh[2];
+};
+__global__ void __launch_bounds__(128)
+gru_step_bwd_kernel(GruBwd p, const float* __restrict__ dout, const float* __restrict__ out,
+                    const float* __restrict__ gates, float* __restrict__ carry, int T, int N, int step) {
+  const int d = blockIdx.y;
+  // backward visits time in the reverse of the forward order of this direction
+  const int t = d == 0 ? T - 1 - step : step;
+  const int tnext = d == 0 ? t + 1 : t - 1;  // the step processed just before (later in forward order)
+  const int tprev = d == 0 ? t - 1 : t + 1;  // source of h_prev in forward order
+  const int k = blockIdx.x * 4 + (threadIdx.x & 3);
+  const int n0 = (blockIdx.z * 32 + (threadIdx.x >> 2)) * 2;
+  if (n0 >= N) return;
+  const bool two = n0 + 1 < N;
+  const int n1 = two ? n0 + 1 : n0;
+  float acc[2] = {0.f, 0.f};
+  if (step > 0) {
+    const float4* g0 = reinterpret_cast<const float4*>(p.dgh[d] + ((size_t)tnext * N + n0) * 768);
+    const float4* g1 = reinterpret_cast<const float4*>(p.dgh[d] + ((size_t)tnext * N + n1) * 768);
+    const float4* w = reinterpret_cast<const float4*>(p.whhT[d] + (size_t)k * 768);
+#pragma unroll 4
+    for (int j4 = 0; j4 < 768 / 4; ++j4) {
+      const float4 a = g0[j4], b = g1[j4], w4 = __ldg(w + j4);
+      acc[0] = fmaf(a.x, w4.x, fmaf(a.y, w4.y, fmaf(a.z, w4.z, fmaf(a.w, w4.w, acc[0]))));
+      acc[1] = fmaf(b.x, w4.x, fmaf(b.y, w4.y, fmaf(b.z, w4.z, fmaf(b.w, w4.w, acc[1]))));
+    }
+  }
+  const bool has_prev = tprev >= 0 && tprev < T;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (q == 1 && !two) break;
+    const int n = q == 0 ? n0 : n1;
+    float* cr = carry + ((size_t)d * N + n) * GH + k;
+    float dh = dout[((size_t)t * N + n) * 512 + d * GH + k] + acc[q];
+    if (step > 0) dh += *cr;
+    const float* gs = gates + (((size_t)t * N + n) * 2 + d) * 4 * GH;
+    const float r = gs[k], z = gs[GH + k], nn = gs[2 * GH + k], ghn = gs[3 * GH + k];
+    const float hp = has_prev ? out[((size_t)tprev * N + n) * 512 + d * GH + k] : 0.f;
+    const float dn = dh * (1.f - z) * (1.f - nn * nn);
+    const float dz = dh * (hp - nn) * z * (1.f - z);
+    const float dr = dn * ghn * r * (1.f - r);
+    float* gi = p.dgi[d] + ((size_t)t * N + n) * 768;
+    float* gh = p.dgh[d] + ((size_t)t * N + n) * 768;
+    gi[k] = dr; gi[GH + k] = dz; gi[2 * GH + k] = dn;
+    gh[k] = dr; gh[GH + k] = dz; gh[2 * GH + k] = dn * r;
+    *cr = dh * z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LogSoftmax over the last dim, one warp per row (models.py:250), and its backward.
+__global__ void log_softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + (size_t)row * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, xr[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(xr[c] - m);
+  s = warp_sum(s);
+  const float lse = m + logf(s);
+  for (int c = lane; c < C; c += 32) y[(size_t)row * C + c] = xr[c] - lse;
+}
+__global__ void log_softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g,
+                                       float* __restrict__ dx, int R, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += g[(size_t)row * C + c];
+  s = warp_sum(s);
+  for (int c = lane; c < C; c += 32)
+    dx[(size_t)row * C + c] = g[(size_t)row * C + c] - expf(y[(size_t)row * C + c]) * s;
+}
+
+// dst[c][r] = src[r][c] (small weight transposes)
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (r0 + i < R && c < C) tile[i][threadIdx.x] = src[(size_t)(r0 + i) * C + c];
+  __syncthreads();
+  const int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (c0 + i < C && r < R) dst[(size_t)(c0 + i) * R + r] = tile[threadIdx.x][i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int ocrs_rec_conv0_fwd(const float* x, int N, int H, int W, const float* w, const float* bias, float* out,
+                       void* stream) {
+  OCRS_CHECK_ARG(H >= 2 && W >= 2, "conv0_fwd: input too small");
+  const long long total = (long long)N * (H / 2) * (W / 2) * 4;
+  conv0_fwd_kernel<<<ocrs_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, w, bias, out);
+  OCRS_CHECK_LAUNCH("conv0_fwd_kernel");
+  return 0;
+}
+
+int ocrs_rec_conv0_bwd_blocks(void) { return 4 * OCRS_NUM_SMS; }
+// partials: [blocks][32][10]
+int ocrs_rec_conv0_bwd(const float* x, int N, int H, int W, const float* w, const float* bias,
+                       const float* dout, float* partials, void* stream) {
+  conv0_bwd_kernel<<<ocrs_rec_conv0_bwd_blocks(), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, w, bias, dout, partials);
+  OCRS_CHECK_LAUNCH("conv0_bwd_kernel");
+  return 0;
+}
+
+static int make_geom(PoolGeom& g, int N, int H, int W, int C, int ph, int pw, int mode, int relu,
+                     long long son, long long soh, long long sow) {
+  OCRS_CHECK_ARG(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0, "bn_act_pool: unsupported channel count %d", C);
+  OCRS_CHECK_ARG(ph * pw <= MAXWIN && ph >= 1 && pw >= 1, "bn_act_pool: window %dx%d too large", ph, pw);
+  g = PoolGeom{N, H, W, C, ph, pw, H / ph, W / pw, mode, relu, son, soh, sow};
+  OCRS_CHECK_ARG(g.Hp > 0 && g.Wp > 0, "bn_act_pool: input smaller than the window");
+  return 0;
+}
+
+int ocrs_rec_bn_act_pool_fwd(const float* y, int N, int H, int W, int C, int ph, int pw, int mode, int relu,
+                             const float* sc, const float* sh, float* out, long long son, long long soh,
+                             long long sow, void* stream) {
+  PoolGeom g;
+  if (make_geom(g, N, H, W, C, ph, pw, mode, relu, son, soh, sow)) return -1;
+  const long long total = (long long)N * g.Hp * g.Wp * (C / 4);
+  bn_act_pool_fwd_kernel<<<ocrs_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y, g, sc, sh, out);
+  OCRS_CHECK_LAUNCH("bn_act_pool_fwd_kernel");
+  return 0;
+}
+
+int ocrs_rec_pool_bwd_blocks(void) { return 4 * OCRS_NUM_SMS; }
+// partials: [blocks][2][C]
+int ocrs_rec_bn_act_pool_bwd_reduce(const float* y, int N, int H, int W, int C, int ph, int pw, int mode,
+                                    int relu, const float* sc, const float* sh, const float* mean,
+                                    const float* invstd, const float* dout, long long son, long long soh,
+                                    long long sow, float* partials, void* stream) {
+  PoolGeom g;
+  if (make_geom(g, N, H, W, C, ph, pw, mode, relu, son, soh, sow)) return -1;
+  const int lanes = 256 / (C / 4);
+  const size_t smem = (size_t)lanes * 2 * C * sizeof(float);
+  OCRS_CHECK_ARG(smem <= 48 * 1024, "bn_act_pool_bwd_reduce: smem");
+  bn_act_pool_bwd_reduce_kernel<<<ocrs_rec_pool_bwd_blocks(), 256, smem, (cudaStream_t)stream>>>(
+      y, g, sc, sh, mean, invstd, dout, partials);
+  OCRS_CHECK_LAUNCH("bn_act_pool_bwd_reduce_kernel");
+  return 0;
+}
+
+int ocrs_rec_bn_act_pool_bwd_apply(const float* y, int N, int H, int W, int C, int ph, int pw, int mode,
+                                   int relu, const float* sc, const float* sh, const float* k1,
+                                   const float* k2, const float* k3, const float* dout, long long son,
+                                   long long soh, long long sow, float* dy, void* stream) {
+  PoolGeom g;
+  if (make_geom(g, N, H, W, C, ph, pw, mode, relu, son, soh, sow)) return -1;
+  const long long total = (long long)N * H * W * (C / 4);
+  bn_act_pool_bwd_apply_kernel<<<ocrs_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y, g, sc, sh, k1, k2, k3,
+                                                                                      dout, dy);
+  OCRS_CHECK_LAUNCH("bn_act_pool_bwd_apply_kernel");
+  return 0;
+}
+
+int ocrs_relu_bwd(const float* act, float* grad, long long n, void* stream) {
+  OCRS_CHECK_ARG(n % 4 == 0, "relu_bwd: length must be a multiple of 4");
+  relu_bwd_kernel<<<ocrs_cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(act, grad, n / 4);
+  OCRS_CHECK_LAUNCH("relu_bwd_kernel");
+  return 0;
+}
+
+// Runs all T steps of one bidirectional GRU layer. gi_f/gi_r: [T*N][768]; whh_*: [768][256].
+int ocrs_gru_layer_fwd(const float* gi_f, const float* gi_r, const float* whh_f, const float* whh_r,
+                       const float* bhh_f, const float* bhh_r, float* out, float* gates, int T, int N,
+                       void* stream) {
+  OCRS_CHECK_ARG(T > 0 && N > 0, "gru_layer_fwd: bad dims");
+  GruDirs p{{gi_f, gi_r}, {whh_f, whh_r}, {bhh_f, bhh_r}};
+  dim3 grid(GH / 4, 2, ocrs_cdiv(N, 64));
+  for (int s = 0; s < T; ++s)
+    gru_step_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, out, gates, T, N, s);
+  OCRS_CHECK_LAUNCH_N("gru_step_fwd_kernel", T);
+  return 0;
+}
+
+// whhT_*: transposed recurrent weights [256][768]; carry: [2][N][256] scratch.
+int ocrs_gru_layer_bwd(const float* whhT_f, const float* whhT_r, const float* dout, const float* out,
+                       const float* gates, float* dgi_f, float* dgi_r, float* dgh_f, float* dgh_r,
+                       float* carry, int T, int N, void* stream) {
+  GruBwd p{{whhT_f, whhT_r}, {dgi_f, dgi_r}, {dgh_f, dgh_r}};
+  dim3 grid(GH / 4, 2, ocrs_cdiv(N, 64));
+  for (int s = 0; s < T; ++s)
+    gru_step_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, dout, out, gates, carry, T, N, s);
+  OCRS_CHECK_LAUNCH_N("gru_step_bwd_kernel", T);
+  return 0;
+}
+
+int ocrs_log_softmax_fwd(const float* x, float* y, int R, int C, void* stream) {
+  log_softmax_fwd_kernel<<<ocrs_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(x, y, R, C);
+  OCRS_CHECK_LAUNCH("log_softmax_fwd_kernel");
+  return 0;
+}
+int ocrs_log_softmax_bwd(const float* y, const float* g, float* dx, int R, int C, void* stream) {
+  log_softmax_bwd_kernel<<<ocrs_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(y, g, dx, R, C);
+  OCRS_CHECK_LAUNCH("log_softmax_bwd_kernel");
+  return 0;
+}
+
+int ocrs_transpose(const float* src, float* dst, int R, int C, void* stream) {
+  dim3 grid(ocrs_cdiv(C, 32), ocrs_cdiv(R, 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, R, C);
+  OCRS_CHECK_LAUNCH("transpose_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+"""Execution plan of the recognition CRNN on the sm_100a kernels (csrc/rec.cu, gemm.cu).
+
+Follows reference ``RecognitionModel.forward`` (ocrs_models/models.py:253-268): conv stack
+(models.py:179-243) in NHWC, permute to (W', N, C) for free in the last pooling kernel's store,
+2-layer bidirectional GRU in fp32 (the reference also forces fp32 there, models.py:264-266),
+Linear + LogSoftmax. One ``torch.autograd.Function`` for the whole model; its backward runs the
+hand-written BPTT / dgrad / wgrad kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+TARGET_BLOCKS = 2 * 148
+
+
+def _empty(shape, dev):
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
+def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bias=None, relu=False,
+         accumulate=False, stats=None, split_ok=False):
+    """C[M,N] = op(A) op(B) through ocrs_gemm. A/B are tensors or raw pointers. With `split_ok` the
+    reduction is split over K when the output has too few tiles to fill the GPU."""
+    dev = out.device if out is not None else (A.device if isinstance(A, torch.Tensor) else None)
+    pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
+    pb = B.data_ptr() if isinstance(B, torch.Tensor) else B
+    if out is None:
+        out = _empty((M, N), dev)
+    if ldc is None:
+        ldc = N
+    lib = _lib.lib()
+    splits = 1
+    if split_ok:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        want = max(1, min(TARGET_BLOCKS // tiles, K // 256))
+        splits = lib.ocrs_gemm_splits(K, want)
+    if splits == 1:
+        call("ocrs_gemm", pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(out), ldc, M, N, K, ptr(bias),
+             int(relu), int(accumulate), ptr(stats), 1, st)
+    else:
+        assert ldc == N and bias is None and not relu and not accumulate and stats is None
+        part = _empty((splits, M, N), out.device)
+        call("ocrs_gemm", pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(part), N, M, N, K, None, 0, 0, None,
+             splits, st)
+        call("ocrs_finalize_partials", ptr(part), splits, M * N, ptr(out), st)
+    return out
+
+
+def colsum(A, lda, M, N, st, dev):
+    lib = _lib.lib()
+    rows = lib.ocrs_colsum_rows(M)
+    part = _empty((rows, N), dev)
+    pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
+    call("ocrs_colsum", pa, lda, M, N, ptr(part), st)
+    out = _empty((N,), dev)
+    call("ocrs_finalize_partials", ptr(part), rows, N, ptr(out), st)
+    return out
+
+
+def im2col(x, N, H, W, C, kh, kw, ph, pw, st):
+    Ho, Wo = H + 2 * ph - kh + 1, W + 2 * pw - kw + 1
+    col = _empty((N * Ho * Wo, kh * kw * C), x.device)
+    call("ocrs_im2col_nhwc", ptr(x), N, H, W, C, kh, kw, ph, pw, Ho, Wo, ptr(col), st)
+    return col, Ho, Wo
+
+
+def _w_fwd(w):
+    """[Cout, Cin, kh, kw] -> [Cout, (ky, kx, ci)] matching the im2col column order."""
+    return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def _w_dgrad(w):
+    """[Cout, Cin, kh, kw] -> [Cin, (ky', kx', co)] with the kernel flipped (correlation of dY)."""
+    return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous()
+
+
+def _w_grad_back(dwp, w):
+    """[Cout, (ky, kx, ci)] -> parameter layout [Cout, Cin, kh, kw]."""
+    co, ci, kh, kw = w.shape
+    return dwp.reshape(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+
+
+class _BNState:
+    def __init__(self, bn, dev):
+        self.bn = bn
+        self.buf = _empty((5, bn.num_features), dev)  # scale, shift, lo(unused), mean, invstd
+
+    @property
+    def scale(self):
+        return self.buf[0]
+
+    @property
+    def shift(self):
+        return self.buf[1]
+
+    @property
+    def mean(self):
+        return self.buf[3]
+
+    @property
+    def invstd(self):
+        return self.buf[4]
+
+
+def _bn_finalize(bn, stats, rows, count, training, relu, st, dev):
+    s = _BNState(bn, dev)
+    C = bn.num_features
+    call("ocrs_bn_finalize", ptr(stats), rows, C, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+         ptr(bn.running_var), BN_MOMENTUM, BN_EPS, int(training), int(relu), ptr(s.buf[0]), ptr(s.buf[1]),
+         ptr(s.buf[2]), ptr(s.buf[3]), ptr(s.buf[4]), st)
+    if training:
+        bn.num_batches_tracked.add_(1)
+    return s
+
+
+class _RecFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        dev = x.device
+        training = model.training
+        N, _, H, W = x.shape
+        st = _lib.stream_ptr(dev)
+        lib = _lib.lib()
+        cv = model.conv
+        save = any(ctx.needs_input_grad)
+        rec = {}
+        with torch.cuda.device(dev):
+            # conv.0 + ReLU + MaxPool2 -> NHWC [N, H/2, W/2, 32]
+            H1, W1 = H // 2, W // 2
+            a0 = _empty((N, H1, W1, 32), dev)
+            call("ocrs_rec_conv0_fwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(a0), st)
+
+            def conv_bn_pool(inp, Hh, Ww, cin, conv, bn, ph, pw, mode, relu, kh=3, pad=1, out_strides=None, out=None):
+                col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, kh, kh, pad, pad, st)
+                M = N * Ho * Wo
+                cout = conv.out_channels
+                rows = lib.ocrs_gemm_stat_rows(M)
+                stats = _empty((rows, 2, cout), dev) if training else None
+                y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1], st,
+                         stats=stats)
+                bs = _bn_finalize(bn, stats, rows, M, training, relu, st, dev)
+                Hp, Wp = Ho // ph, Wo // pw
+                if out is None:
+                    out = _empty((N, Hp, Wp, cout), dev)
+                    out_strides = (Hp * Wp * cout, Wp * cout, cout)
+                call("ocrs_rec_bn_act_pool_fwd", ptr(y), N, Ho, Wo, cout, ph, pw, mode, int(relu), ptr(bs.scale),
+                     ptr(bs.shift), ptr(out), *out_strides, st)
+                return out, Hp, Wp, dict(col=col, y=y, bs=bs, geom=(Ho, Wo, cout, ph, pw, mode, int(relu)),
+                                         ostr=out_strides, inp_geom=(Hh, Ww, cin), k=(kh, pad))
+
+            def conv_bias_relu(inp, Hh, Ww, cin, conv):
+                col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, 3, 3, 1, 1, st)
+                M = N * Ho * Wo
+                a = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, conv.out_channels,
+                         col.shape[1], st, bias=conv.bias, relu=True)
+                return a, dict(col=col, a=a, inp_geom=(Hh, Ww, cin))
+
+            a3, H3, W3, rec["3"] = conv_bn_pool(a0, H1, W1, 32, cv["3"], cv["4"], 2, 2, 0, True)
+            a7, rec["7"] = conv_bias_relu(a3, H3, W3, 64, cv["7"])
+            a9, H9, W9, rec["9"] = conv_bn_pool(a7, H3, W3, 128, cv["9"], cv["10"], 2, 1, 0, True)
+            a13, rec["13"] = conv_bias_relu(a9, H9, W9, 128, cv["13"])
+            a15, H15, W15, rec["15"] = conv_bn_pool(a13, H9, W9, 128, cv["15"], cv["16"], 2, 1, 0, True)
+            # conv.19 (2x2, pad 1) + BN + AvgPool((4,1)) stored directly as (T, N, C*H') with H' = 1
+            Ho19, T = H15 + 1, W15 + 1
+            if Ho19 // 4 != 1:
+                raise RuntimeError(f"RecognitionModel expects input height 64 (got {H}): C*H' must stay 128")
+            seq = _empty((T, N, 128), dev)
+            _, _, _, rec["19"] = conv_bn_pool(a15, H15, W15, 128, cv["19"], cv["20"], 4, 1, 1, False, kh=2, pad=1,
+                                              out_strides=(128, 0, N * 128), out=seq)
+            # 2-layer bidirectional GRU
+            gru = model.gru
+            TN = T * N
+            layer_in = seq
+            gru_rec = []
+            for layer in range(2):
+                isz = 128 if layer == 0 else 512
+                gi = []
+                for sfx in ("", "_reverse"):
+                    w_ih = getattr(gru, f"weight_ih_l{layer}{sfx}")
+                    b_ih = getattr(gru, f"bias_ih_l{layer}{sfx}")
+                    gi.append(gemm(layer_in, isz, True, w_ih, isz, True, TN, 768, isz, st, bias=b_ih))
+                out = _empty((T, N, 512), dev)
+                gates = _empty((T, N, 2, 4, 256), dev)
+                call("ocrs_gru_layer_fwd", ptr(gi[0]), ptr(gi[1]), ptr(getattr(gru, f"weight_hh_l{layer}")),
+                     ptr(getattr(gru, f"weight_hh_l{layer}_reverse")), ptr(getattr(gru, f"bias_hh_l{layer}")),
+                     ptr(getattr(gru, f"bias_hh_l{layer}_reverse")), ptr(out), ptr(gates), T, N, st)
+                gru_rec.append(dict(x=layer_in, out=out, gates=gates, isz=isz))
+                layer_in = out
+            lin = model.output[0]
+            C = lin.out_features
+            logits = gemm(layer_in, 512, True, lin.weight, 512, True, TN, C, 512, st, bias=lin.bias)
+            lp = _empty((T, N, C), dev)
+            call("ocrs_log_softmax_fwd", ptr(logits), ptr(lp), TN, C, st)
+        if save:
+            ctx.model = model
+            ctx.rec = rec
+            ctx.gru_rec = gru_rec
+            ctx.misc = (x, a0, lp, N, H, W, T, C)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g_lp):
+        model = ctx.model
+        rec, gru_rec = ctx.rec, ctx.gru_rec
+        x, a0, lp, N, H, W, T, C = ctx.misc
+        dev = lp.device
+        st = _lib.stream_ptr(dev)
+        lib = _lib.lib()
+        cv, gru, lin = model.conv, model.gru, model.output[0]
+        TN = T * N
+        grads = {}
+        g_lp = g_lp.contiguous().float()
+        with torch.cuda.device(dev):
+            dlog = _empty((TN, C), dev)
+            call("ocrs_log_softmax_bwd", ptr(lp), ptr(g_lp), ptr(dlog), TN, C, st)
+            out1 = gru_rec[1]["out"]
+            grads[id(lin.weight)] = gemm(dlog, C, False, out1, 512, False, C, 512, TN, st, split_ok=True)
+            grads[id(lin.bias)] = colsum(dlog, C, TN, C, st, dev)
+            d_out = gemm(dlog, C, True, lin.weight, 512, False, TN, 512, C, st)
+            for layer in (1, 0):
+                r = gru_rec[layer]
+                isz, xin, out, gates = r["isz"], r["x"], r["out"], r["gates"]
+                names = [f"l{layer}", f"l{layer}_reverse"]
+                whhT = []
+                for nm in names:
+                    t_ = _empty((256, 768), dev)
+                    call("ocrs_transpose", ptr(getattr(gru, "weight_hh_" + nm)), ptr(t_), 768, 256, st)
+                    whhT.append(t_)
+                dgi = [_empty((TN, 768), dev) for _ in range(2)]
+                dgh = [_empty((TN, 768), dev) for _ in range(2)]
+                carry = _empty((2, N, 256), dev)
+                call("ocrs_gru_layer_bwd", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates), ptr(dgi[0]),
+                     ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), ptr(carry), T, N, st)
+                d_in = _empty((TN, isz), dev)
+                for d, nm in enumerate(names):
+                    w_ih = getattr(gru, "weight_ih_" + nm)
+                    grads[id(w_ih)] = gemm(dgi[d], 768, False, xin, isz, False, 768, isz, TN, st, split_ok=True)
+                    grads[id(getattr(gru, "bias_ih_" + nm))] = colsum(dgi[d], 768, TN, 768, st, dev)
+                    grads[id(getattr(gru, "bias_hh_" + nm))] = colsum(dgh[d], 768, TN, 768, st, dev)
+                    # dW_hh = sum_t dgh[t]^T h_prev[t]; h_prev[t] = out[t-1] (fwd) / out[t+1] (reverse)
+                    rows = (T - 1) * N
+                    if rows > 0:
+                        if d == 0:
+                            pa = dgh[d].data_ptr() + 4 * N * 768
+                            pb = out.data_ptr()
+                        else:
+                            pa = dgh[d].data_ptr()
+                            pb = out.data_ptr() + 4 * (N * 512 + 256)
+                        dwhh = _empty((768, 256), dev)
+                        gemm(pa, 768, False, pb, 512, False, 768, 256, rows, st, out=dwhh, split_ok=True)
+                    else:
+                        dwhh = torch.zeros((768, 256), device=dev)
+                    grads[id(getattr(gru, "weight_hh_" + nm))] = dwhh
+                    gemm(dgi[d], 768, True, w_ih, isz, False, TN, isz, 768, st, out=d_in, accumulate=(d == 1))
+                d_out = d_in
+            d_seq = d_out  # [T, N, 128]
+
+            def bn_pool_bwd(r, conv, bn, dout, dstr):
+                Ho, Wo, cout, ph, pw, mode, relu = r["geom"]
+                bs, y = r["bs"], r["y"]
+                blocks = lib.ocrs_rec_pool_bwd_blocks()
+                part = _empty((blocks, 2, cout), dev)
+                call("ocrs_rec_bn_act_pool_bwd_reduce", ptr(y), N, Ho, Wo, cout, ph, pw, mode, relu, ptr(bs.scale),
+                     ptr(bs.shift), ptr(bs.mean), ptr(bs.invstd), ptr(dout), *dstr, ptr(part), st)
+                coef = _empty((5, cout), dev)
+                call("ocrs_bn_bwd_finalize", ptr(part), blocks, cout, float(N * Ho * Wo), ptr(bn.weight), ptr(bs.mean),
+                     ptr(bs.invstd), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), st)
+                grads[id(bn.weight)] = coef[0].clone()
+                grads[id(bn.bias)] = coef[1].clone()
+                dy = _empty((N, Ho, Wo, cout), dev)
+                call("ocrs_rec_bn_act_pool_bwd_apply", ptr(y), N, Ho, Wo, cout, ph, pw, mode, relu, ptr(bs.scale),
+                     ptr(bs.shift), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), ptr(dout), *dstr, ptr(dy), st)
+                return dy, Ho, Wo
+
+            def conv_bwd(r, conv, dy, Ho, Wo, need_dx=True):
+                """dy: [N, Ho, Wo, Cout] gradient of the raw conv output. Returns d(input) NHWC."""
+                col = r["col"]
+                M, K = col.shape
+                cout = conv.out_channels
+                dwp = gemm(dy, cout, False, col, K, False, cout, K, M, st, split_ok=True)
+                grads[id(conv.weight)] = _w_grad_back(dwp, conv.weight)
+                if conv.bias is not None:
+                    grads[id(conv.bias)] = colsum(dy, cout, M, cout, st, dev)
+                if not need_dx:
+                    return None
+                Hh, Ww, cin = r["inp_geom"]
+                kh, pad = r.get("k", (3, 1))
+                dcol, Hi, Wi = im2col(dy, N, Ho, Wo, cout, kh, kh, kh - 1 - pad, kh - 1 - pad, st)
+                assert (Hi, Wi) == (Hh, Ww)
+                return gemm(dcol, dcol.shape[1], True, _w_dgrad(conv.weight), dcol.shape[1], True, N * Hh * Ww, cin,
+                            dcol.shape[1], st)
+
+            r = rec["19"]
+            dy, Ho, Wo = bn_pool_bwd(r, cv["19"], cv["20"], d_seq, r["ostr"])
+            d_a15 = conv_bwd(r, cv["19"], dy, Ho, Wo)
+
+            def stage(key_bn, key_relu, d_act, bn_name):
+                """[conv+bias+ReLU] -> [conv+BN+ReLU+pool] pair, backwards. d_act: grad of the pooled output."""
+                rb = rec[key_bn]
+                Ho_, Wo_, cout, ph, pw, _, _ = rb["geom"]
+                Hp, Wp = Ho_ // ph, Wo_ // pw
+                dy_, Ho2, Wo2 = bn_pool_bwd(rb, cv[key_bn], cv[bn_name], d_act, (Hp * Wp * cout, Wp * cout, cout))
+                d_prev = conv_bwd(rb, cv[key_bn], dy_, Ho2, Wo2)
+                if key_relu is None:
+                    return d_prev
+                rr = rec[key_relu]
+                call("ocrs_relu_bwd", ptr(rr["a"]), ptr(d_prev), d_prev.numel(), st)
+                Hh, Ww, _ = rb["inp_geom"]
+                return conv_bwd(rr, cv[key_relu], d_prev, Hh, Ww)
+
+            d_a9 = stage("15", "13", d_a15, "16")
+            d_a3 = stage("9", "7", d_a9, "10")
+            d_a0 = stage("3", None, d_a3, "4")
+            blocks = lib.ocrs_rec_conv0_bwd_blocks()
+            part = _empty((blocks, 32, 10), dev)
+            call("ocrs_rec_conv0_bwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(d_a0), ptr(part), st)
+            wb = _empty((32, 10), dev)
+            call("ocrs_finalize_partials", ptr(part), blocks, 320, ptr(wb), st)
+            grads[id(cv["0"].weight)] = wb[:, :9].reshape(32, 1, 3, 3).contiguous()
+            grads[id(cv["0"].bias)] = wb[:, 9].contiguous()
+        ctx.rec = ctx.gru_rec = ctx.misc = None
+        return (None, None) + tuple(grads.get(id(p)) for p in model.parameters())
+
+
+def recognition_forward(model, x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("ocrs_models_b200.RecognitionModel has no CPU path: input must be a CUDA tensor")
+    if x.dim() != 4 or x.shape[1] != 1:
+        raise RuntimeError(f"expected (N, 1, 64, W) input, got {tuple(x.shape)}")
+    if x.shape[3] < 4:
+        raise RuntimeError("input width must be at least 4")
+    x = x.float().contiguous()
+    return _RecFunction.apply(model, x, *model.parameters())
