@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the two training hot paths (BASELINE.json): lines/s of the recognition CRNN train
+step at 64x800 batch 64 per GPU (headline line) and images/s of the detection train step at
+1024x1024 batch 32 per GPU (reported under "det"). One step = fwd + loss + bwd + (clip) + Adam.
+
+    python bench.py --gpus N --steps K --warmup W            # N > 1: launched through torchrun
+    python bench.py --impl reference ...                     # the CPU path (oracle port) on host cores
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+REC = dict(n=64, h=64, w=800, s_pad=64, s=40, il=200)
+DET = dict(n=32, h=1024, w=1024)
+REC_FLOP_PER_LINE = 11.17e9  # 714.9 GFLOP / 64 lines (fwd + dgrad + wgrad)
+DET_BYTES_PER_IMG_FP32 = 2 * 1.655e9  # SURVEY 8d fused-block model, fp32 storage
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def make_batch(kind: str, rank: int, device, n: int | None = None):
+    g = torch.Generator().manual_seed(1234 + rank)
+    if kind == "rec":
+        n = n or REC["n"]
+        return {
+            "image": torch.rand(n, 1, REC["h"], REC["w"], generator=g) - 0.5,
+            "targets": torch.randint(1, 97, (n, REC["s_pad"]), generator=g, dtype=torch.int32),
+            "input_lengths": torch.full((n,), REC["il"], dtype=torch.int64),
+            "target_lengths": torch.full((n,), REC["s"], dtype=torch.int64),
+        }
+    n = n or DET["n"]
+    return {
+        "image": torch.rand(n, 1, DET["h"], DET["w"], generator=g) - 0.5,
+        "mask": (torch.rand(n, 1, DET["h"], DET["w"], generator=g) < 0.10).float(),
+    }
+
+
+class Workload:
+    """Model + fused optimiser + one synthetic batch (pinned on the host, resident on the device)."""
+
+    def __init__(self, kind, device, rank, world, group=None):
+        from ocrs_models_b200 import CTCLoss, DetectionModel, RecognitionModel, balanced_cross_entropy_loss
+        from ocrs_models_b200.optim import FusedAdam
+        from oracle.functional import DEFAULT_ALPHABET
+
+        self.kind, self.device = kind, device
+        torch.manual_seed(1234)  # train_detection.py:337-338
+        if kind == "rec":
+            self.model = RecognitionModel(DEFAULT_ALPHABET).to(device).train()
+            self.opt = FusedAdam(self.model, lr=1e-3, max_grad_norm=4.0, process_group=group, world_size=world)
+            self.loss_fn = CTCLoss()
+        else:
+            self.model = DetectionModel().to(device).train()
+            self.opt = FusedAdam(self.model, lr=1e-3, process_group=group, world_size=world)
+            self.loss_fn = balanced_cross_entropy_loss
+        self.host = {k: v.pin_memory() for k, v in make_batch(kind, rank, device).items()}
+        self.dev = {k: v.to(device) for k, v in self.host.items()}
+        self.units = self.host["image"].shape[0]
+        self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in self.host.items() if k in ("image", "mask", "targets"))
+
+    def step(self, batch):
+        self.opt.zero_grad()
+        if self.kind == "rec":
+            lp = self.model(batch["image"])
+            loss = self.loss_fn(lp, batch["targets"], batch["input_lengths"], batch["target_lengths"])
+        else:
+            loss = self.loss_fn(self.model(batch["image"]), batch["mask"])
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def step_resident(self):
+        return self.step(self.dev)
+
+    def step_e2e(self):
+        """Public-API step from HOST buffers: H2D of the inputs, the step, D2H of the loss."""
+        b = dict(self.host)
+        for k in ("image", "mask", "targets"):
+            if k in b:
+                b[k] = b[k].to(self.device, non_blocking=True)
+        return float(self.step(b).item())
+
+
+def timed(fn, steps, warmup, device, dist_on):
+    for _ in range(warmup):
+        fn()
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    wall = (time.perf_counter() - t0) * 1e3
+    if dist_on:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, wall], device=device, dtype=torch.float64)
+    if dist_on:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t[0]), float(t[1])
+
+
+def kernel_profile(wl: Workload, steps=2):
+    """Per-entry-point device time of the step, CUDA events on the launching stream."""
+    from ocrs_models_b200 import _lib
+
+    _lib.PROFILE = {}
+    for _ in range(steps):
+        wl.step_resident()
+    torch.cuda.synchronize(wl.device)
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    out = {}
+    for name, evs in prof.items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+        meta = sum(m for _, _, m in evs if m is not None)
+        out[name] = dict(ms=ms / steps, calls=len(evs) // steps, meta=meta / steps)
+    return out
+
+
+def roofline(kind, prof, pk):
+    total = sum(v["ms"] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    name, v = top
+    share = v["ms"] / total if total else 0.0
+    if name == "ocrs_gemm":
+        ach = v["meta"] / (v["ms"] * 1e-3) / 1e12
+        return dict(bound="tensor", kernel=name, achieved=ach, peak=pk["tf_sus"], unit="TFLOP/s", frac=ach / pk["tf_sus"],
+                    traffic=None, share_of_step=share, launches_per_step=v["calls"], peak_source=pk["src"] + " bf16 sustained",
+                    note="fp32 CUDA-core GEMM (parity mode) measured against the bf16 tensor-pipe peak")
+    ach = v["meta"] / (v["ms"] * 1e-3) / 1e9 if v["meta"] else None
+    return dict(bound="hbm", kernel=name, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=(ach / pk["hbm"]) if ach else None,
+                traffic=None, share_of_step=share, launches_per_step=v["calls"], peak_source=pk["src"])
+
+
+def cpu_reference_step(kind, n, threads):
+    """The reference's CPU path (oracle port of models.py + losses + clip + Adam), fp32."""
+    from ocrs_models_b200 import DetectionModel, RecognitionModel
+    from oracle import functional as O
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    model = RecognitionModel(O.DEFAULT_ALPHABET) if kind == "rec" else DetectionModel()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    batch = make_batch(kind, 0, "cpu", n)
+    state: dict = {}
+
+    def step():
+        _, loss, grads, nb = O.train_step_grads(kind, sd, batch)
+        if kind == "rec":
+            O.clip_grad_norm(grads, 4.0)
+        O.adam_step({k: sd[k] for k in grads}, grads, state)
+        sd.update(nb)
+        return float(loss)
+
+    return step
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.
+    The reference is Python/PyTorch and /root/reference does not travel to the GPU box, so this
+    runs the oracle port (kind = "port") with all host threads on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    kind = args.workload
+    n = 8 if kind == "rec" else 1
+    step = cpu_reference_step(kind, n, threads)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = n / dt
+    unit = "lines/s" if kind == "rec" else "images/s"
+    shape = "64x800 lines" if kind == "rec" else "1024x1024 images"
+    sample = f"{n} {shape} per step, {steps} timed steps after 1 warm-up, fp32, torch CPU ops"
+    print(json.dumps({
+        "impl": "reference", "metric": f"train {unit.split('/')[0]}/sec", "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(kind), "batch_per_step": n, "host_threads": threads},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(kind):
+    if kind == "rec":
+        return "text-recognition CRNN training, synthetic 64x800 line images, batch 64 per GPU, CTC loss (BASELINE configs[1])"
+    return "text-detection segmentation training, synthetic 1024x1024 greyscale, batch 32 per GPU, balanced BCE (BASELINE configs[2])"
+
+
+def measure(kind, args, device, rank, world, dist_on, pk):
+    from ocrs_models_b200 import _lib
+
+    wl = Workload(kind, device, rank, world)
+    lib = _lib.lib()
+    for _ in range(args.warmup):
+        wl.step_resident()
+    torch.cuda.synchronize(device)
+    l0 = lib.ocrs_launch_count()
+    with ClockSampler(device.index or 0) as cs:
+        ms, _ = timed(wl.step_resident, args.steps, 0, device, dist_on)
+    launches = lib.ocrs_launch_count() - l0
+    _, wall = timed(wl.step_e2e, args.steps, 1, device, dist_on)
+    units = wl.units * world
+    unit = "lines/s" if kind == "rec" else "images/s"
+    res = {
+        "value": units * args.steps / (ms * 1e-3), "unit": unit, "ms_per_step": ms / args.steps,
+        "e2e": {"value": units * args.steps / (wall * 1e-3), "unit": unit, "h2d_bytes_per_step": wl.h2d_bytes,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": cs.summary(),
+    }
+    if rank == 0:
+        prof = kernel_profile(wl)
+        res["roofline"] = roofline(kind, prof, pk)
+        tot = sum(v["ms"] for v in prof.values())
+        res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        res["kernel_ms_total"] = round(tot, 3)
+        if kind == "rec":
+            ach = REC_FLOP_PER_LINE * wl.units / (ms / args.steps * 1e-3) / 1e12
+            res["step_roofline"] = dict(bound="tensor", achieved=ach, peak=pk["tf_sus"], unit="TFLOP/s", frac=ach / pk["tf_sus"])
+        else:
+            ach = DET_BYTES_PER_IMG_FP32 * wl.units / (ms / args.steps * 1e-3) / 1e9
+            res["step_roofline"] = dict(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                                        note="algorithmic bytes of the ideally fused step at fp32 storage (SURVEY 8d)")
+    del wl
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rec", choices=["rec", "det"], help="headline workload of the JSON line")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other workload's sub-object")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist_on = world > 1
+    if dist_on:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    pk = peaks()
+    args.warmup = max(args.warmup, 3)
+    main_res = measure(args.workload, args, device, rank, world, dist_on, pk)
+    other = "det" if args.workload == "rec" else "rec"
+    other_res = None if args.no_secondary else measure(other, args, device, rank, world, dist_on, pk)
+
+    if rank == 0:
+        line = {
+            "metric": "train lines/sec rec@64x800" if args.workload == "rec" else "train images/sec det@1024x1024",
+            "value": main_res["value"], "unit": main_res["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "parallelism": f"dp{world}", "l2": "inputs+activations > L2 (126 MB)",
+                       "precision_mode": "parity (fp32 storage, fp32 FMA contractions)"},
+            "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
+            "roofline": main_res.get("roofline"), "step_roofline": main_res.get("step_roofline"),
+            "kernel_ms_per_step": main_res.get("kernel_ms_per_step"),
+        }
+        if other_res is not None:
+            line[other] = {"metric": "train images/sec det@1024x1024" if other == "det" else "train lines/sec rec@64x800",
+                           "workload": workload_name(other), **other_res}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = 8 if args.workload == "rec" else 1
+            step = cpu_reference_step(args.workload, n, threads)
+            step()
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                step()
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": n / dt, "unit": main_res["unit"], "cores": threads, "kind": "port",
+                                    "sample": f"oracle port of the reference CPU step, batch {n}, {reps} timed steps after 1 warm-up, fp32"}
+        print(json.dumps(line))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@ P, I, F, D, L = c_void_p, c_int, c_float, c_double, c_longlong
 SIGNATURES: dict[str, list] = {
     "ocrs_version": [],
     "ocrs_device_arch": [],
+    "ocrs_launch_count": [],
     "ocrs_ctc_alpha_row": [I],
     "ocrs_ctc_fwd": [P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P],
     "ocrs_ctc_bwd": [P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
@@ -51,6 +52,10 @@ SIGNATURES: dict[str, list] = {
     "ocrs_gemm_stat_rows": [I],
     "ocrs_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_gemm_splits": [I, I],
+    # tcgen05 GEMM (csrc/gemm_tc.cu)
+    "ocrs_gemm_tc_supported": [P, L, P, L],
+    "ocrs_gemm_tc": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
+    "ocrs_gemm_tc_splits": [I, I],
     "ocrs_im2col_nhwc": [P, I, I, I, I, I, I, I, I, I, I, P, P],
     "ocrs_colsum_rows": [I],
     "ocrs_colsum": [P, L, I, I, P, P],
@@ -65,16 +70,22 @@ SIGNATURES: dict[str, list] = {
     "ocrs_relu_bwd": [P, P, L, P],
     "ocrs_gru_layer_fwd": [P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_gru_layer_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
+    "ocrs_gru_layer_fwd_persist": [P, P, P, P, P, P, P, P, I, I, P],
+    "ocrs_gru_layer_bwd_persist": [P, P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_log_softmax_fwd": [P, P, I, I, P],
     "ocrs_log_softmax_bwd": [P, P, P, I, I, P],
     "ocrs_transpose": [P, P, I, I, P],
+    # optimiser glue (csrc/optim.cu)
+    "ocrs_optim_blocks": [],
+    "ocrs_grad_norm": [P, L, F, P, P, P],
+    "ocrs_adam_step": [P, P, P, P, L, F, F, F, F, I, F, F, P, P],
     # balanced BCE (csrc/det_loss.cu)
     "ocrs_bce_state_words": [],
     "ocrs_bce_blocks": [],
     "ocrs_balanced_bce_fwd": [P, P, L, P, P, P, P, P],
     "ocrs_balanced_bce_bwd": [P, P, P, L, P, P, P, P],
 }
-_RESTYPE = {"ocrs_last_error": c_char_p}
+_RESTYPE = {"ocrs_last_error": c_char_p, "ocrs_launch_count": c_longlong}
 
 _lib = None
 
@@ -108,10 +119,23 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
-def call(name: str, *args) -> None:
+# Optional per-entry-point device timing (bench.py's roofline pass): name -> [(start, end, meta)].
+PROFILE: dict | None = None
+
+
+def call(name: str, *args, meta=None) -> None:
     """Invoke an entry point; raise RuntimeError with ocrs_last_error() on failure."""
     l = lib()
-    rc = getattr(l, name)(*args)
+    if PROFILE is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1, meta))
+    else:
+        rc = getattr(l, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {l.ocrs_last_error().decode()}")
 

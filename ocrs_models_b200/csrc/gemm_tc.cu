@@ -1,0 +1,351 @@
+// tcgen05 (5th-gen tensor core) GEMM for the recognition path, fp32 in / fp32 out with fp32-class
+// accuracy through a 3xTF32 split:   a = a_hi + a_lo  (a_hi = a rounded to TF32),
+//   A.B  ~=  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi        (relative error ~2^-21, vs 2^-11 for plain TF32)
+// which is what the 1e-3 gradient parity target of this port needs (SURVEY finding 6).
+//
+// One CTA per 128 x BN output tile (BN in {32, 64, 128}), 192 threads:
+//   warp 0      TMA producer: fp32 operand tiles -> 128B-swizzled shared memory (3 stages)
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, accumulator in TMEM)
+//   warps 2-5   split each landed stage into hi / lo tiles in place, then the epilogue:
+//               tcgen05.ld TMEM -> registers -> (+bias, ReLU) -> smem tile -> coalesced global
+//               stores (+ per-column sum / sum^2 partials for a following BatchNorm)
+// Operands may be K-major (X[rows][K]) or MN-major (X[K][rows]); the latter is what the weight
+// gradients dW = dY^T . X need, and is expressed purely through the TMA boxes and the UMMA
+// shared-memory descriptors (no transposes in HBM). Split-K over gridDim.z.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TBM = 128;          // tile rows (UMMA M)
+constexpr int TBK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int A_TILE_BYTES = TBM * TBK * 4;          // 16 KB
+constexpr int STAGE_BYTES = 4 * A_TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo (B sized for BN = 128)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcArgs {
+  float* C; long long ldc;
+  int M, N, K;
+  const float* bias;
+  int relu, accumulate;
+  float* stats;          // [gridDim.y][2][N] or null
+  int kb_per_split;      // k-blocks per blockIdx.z
+  int a_mn, b_mn;        // operand is MN-major (stored [K][rows])
+  int bn;                // tile columns (UMMA N)
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// UMMA shared-memory descriptor (sm_100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version 1 at [46,48), SWIZZLE_128B = 2 at [61,64).
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only
+// layout the hardware accepts for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  // barriers: full[s] = bar0 + 8 s ; conv[s] = +24 ; empty[s] = +48 ; tmem_full = +72 ; tmem ptr at +80
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 24u + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 48u + 8u * s; };
+  const uint32_t tmem_full_bar = bar0 + 72u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 80);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * g.bn;
+  const int total_kb = (g.K + TBK - 1) / TBK;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+  const int nkb = kb1 - kb0;
+  const uint32_t b_bytes = (uint32_t)g.bn * TBK * 4;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
+        mbar_expect_tx(full_bar(s), A_TILE_BYTES + b_bytes);
+        const int k0 = (kb0 + i) * TBK;
+        if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0, full_bar(s));
+        else
+          for (int c = 0; c < TBM / 32; ++c) tma_load_2d(sa + c * 4096, &map_a, m0 + 32 * c, k0, full_bar(s));
+        if (!g.b_mn) tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
+        else
+          for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(conv_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
+        // K-major (SWIZZLE_128B): 8 rows x 128 B atoms 1024 B apart (SBO), k-step = +32 B inside the row.
+        // MN-major (SWIZZLE_128B_BASE32B): 32-wide MN chunks 4096 B apart (LBO), atoms of 4 k-rows
+        // 512 B apart (SBO), k-step (8 k-rows) = +1024 B.
+        const uint32_t a_lbo = g.a_mn ? 4096u : 16u, b_lbo = g.b_mn ? 4096u : 16u;
+        const uint32_t a_sbo = g.a_mn ? 512u : 1024u, b_sbo = g.b_mn ? 512u : 1024u;
+        const uint32_t a_lt = g.a_mn ? 1u : 2u, b_lt = g.b_mn ? 1u : 2u;
+        const uint32_t a_step = g.a_mn ? 1024u : 32u, b_step = g.b_mn ? 1024u : 32u;
+#pragma unroll
+        for (int ks = 0; ks < TBK / 8; ++ks) {
+          const uint64_t ah = make_desc(sa + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t al = make_desc(sa + A_TILE_BYTES + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t bh = make_desc(sb + ks * b_step, b_lbo, b_sbo, b_lt);
+          const uint64_t bl = make_desc(sb + A_TILE_BYTES + ks * b_step, b_lbo, b_sbo, b_lt);
+          umma_tf32(tmem_base, ah, bh, g.idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, ah, bl, g.idesc, 1u);
+          umma_tf32(tmem_base, al, bh, g.idesc, 1u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- converter: split landed fp32 tiles into TF32-exact hi (in place) and lo ----
+    const int ct = threadIdx.x - 64;  // 0..127
+    const int a_vec = A_TILE_BYTES / 16, b_vec = (int)b_bytes / 16;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      float4* ah = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
+      float4* al = ah + a_vec;
+      float4* bh = al + a_vec;
+      float4* bl = bh + a_vec;
+      auto split = [](float4* hi, float4* lo, int idx) {
+        float4 v = hi[idx], h, l;
+        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
+        hi[idx] = h;
+        lo[idx] = l;
+      };
+      for (int j = ct; j < a_vec; j += 128) split(ah, al, j);
+      for (int j = ct; j < b_vec; j += 128) split(bh, bl, j);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(conv_bar(s));
+    }
+    // ---- epilogue ----
+    mbar_wait(tmem_full_bar, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;         // tile row held by this thread
+    float* ct_s = reinterpret_cast<float*>(base_ptr);  // [128][bn + 1] staging tile
+    const int ldt = g.bn + 1;
+    for (int c0 = 0; c0 < g.bn; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = __uint_as_float(r[j]);
+        const int n = n0 + c0 + j;
+        if (g.bias && n < g.N) v += g.bias[n];
+        if (g.relu) v = fmaxf(v, 0.f);
+        ct_s[row * ldt + c0 + j] = v;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* C = g.C + (size_t)blockIdx.z * g.M * g.ldc;
+    const int ew = warp - 2;  // 0..3: rows ew*32 .. +31
+    for (int rr = 0; rr < 32; ++rr) {
+      const int rloc = ew * 32 + rr, m = m0 + rloc;
+      if (m >= g.M) break;
+      for (int c = lane; c < g.bn; c += 32) {
+        const int n = n0 + c;
+        if (n < g.N) {
+          float v = ct_s[rloc * ldt + c];
+          float* dst = C + (size_t)m * g.ldc + n;
+          if (g.accumulate) { v += *dst; ct_s[rloc * ldt + c] = v; }
+          *dst = v;
+        }
+      }
+    }
+    if (g.stats) {
+      if (g.accumulate) asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ct < g.bn && n0 + ct < g.N) {
+        const int rows = min(TBM, g.M - m0);
+        float s1 = 0.f, s2 = 0.f;
+        for (int rloc = 0; rloc < rows; ++rloc) {
+          const float v = ct_s[rloc * ldt + ct];
+          s1 += v;
+          s2 = fmaf(v, v, s2);
+        }
+        g.stats[((size_t)blockIdx.y * 2) * g.N + n0 + ct] = s1;
+        g.stats[((size_t)blockIdx.y * 2 + 1) * g.N + n0 + ct] = s2;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of stride ld elements.
+int make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_inner,
+             int box_outer, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ocrs_set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return -1; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ocrs_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 when (lda, ldb, pointers) satisfy the TMA constraints of ocrs_gemm_tc.
+int ocrs_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb) {
+  return (lda % 4 == 0) && (ldb % 4 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+}
+
+// Same contract as ocrs_gemm (gemm.cu): a_kmajor: A is [M][K] else [K][M]; b_kmajor: B is [N][K] else [K][N].
+int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor,
+                 float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate,
+                 float* stats, int splits, void* stream) {
+  OCRS_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tc: bad dims %d %d %d", M, N, K);
+  OCRS_CHECK_ARG(ocrs_gemm_tc_supported(A, lda, B, ldb), "gemm_tc: operands must be 16-byte aligned with ld %% 4 == 0");
+  OCRS_CHECK_ARG(splits >= 1, "gemm_tc: bad split count");
+  OCRS_CHECK_ARG(splits == 1 || (!bias && !relu && !accumulate && !stats), "gemm_tc: split-K takes no epilogue");
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  CUtensorMap ma, mb;
+  if (a_kmajor) { if (make_map(&ma, A, K, M, lda, TBK, TBM, false)) return -1; }
+  else          { if (make_map(&ma, A, M, K, lda, 32, TBK, true)) return -1; }
+  if (b_kmajor) { if (make_map(&mb, B, K, N, ldb, TBK, bn, false)) return -1; }
+  else          { if (make_map(&mb, B, N, K, ldb, 32, TBK, true)) return -1; }
+  TcArgs g{C, ldc, M, N, K, bias, relu, accumulate, stats, 0, !a_kmajor, !b_kmajor, bn, 0};
+  const int total_kb = ocrs_cdiv(K, TBK);
+  g.kb_per_split = ocrs_cdiv(total_kb, splits);
+  const int zs = ocrs_cdiv(total_kb, g.kb_per_split);
+  // instruction descriptor: D = F32 (bit 4), A/B = TF32 (2 << 7, 2 << 10), majors, N >> 3 at 17, M >> 4 at 24
+  g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
+            ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  dim3 grid(ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs);
+  gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
+  OCRS_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+
+// Number of [M][ldc] partial products ocrs_gemm_tc writes for a requested split count.
+int ocrs_gemm_tc_splits(int K, int splits) {
+  const int total_kb = ocrs_cdiv(K, TBK);
+  const int per = ocrs_cdiv(total_kb, splits < 1 ? 1 : splits);
+  return ocrs_cdiv(total_kb, per);
+}
+
+}  // extern "C"

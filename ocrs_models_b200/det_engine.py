@@ -71,7 +71,8 @@ class _Sep:
         rows = lib.ocrs_det_dwpw_partial_rows(N, H, W)
         partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
         call("ocrs_det_dwpw_fwd", inp.p, inp.ss, N, self.cin, H, W, *inp.xfp(), ptr(self.dw.weight),
-             ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st)
+             ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st,
+             meta=4.0 * N * H * W * (self.cin + self.cout))
         if xf_dst is None:
             buf = torch.empty((3, self.cout), dtype=torch.float32, device=dev)
             xf_dst = (buf[0], buf[1], buf[2])
@@ -99,17 +100,18 @@ class _Sep:
         part = torch.empty((rows, 2, co), dtype=torch.float32, device=dev)
         ysc, ysh, ylo = y.xfp()
         call("ocrs_bnrelu_bwd_reduce", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, ysc, ysh, ylo, ptr(stats[0]),
-             ptr(stats[1]), ptr(part), st)
+             ptr(stats[1]), ptr(part), st, meta=4.0 * N * HW * 2 * co)
         coef = torch.empty((5, co), dtype=torch.float32, device=dev)  # dgamma, dbeta, k1, k2, k3
         call("ocrs_bn_bwd_finalize", ptr(part), rows, co, float(N * HW), ptr(self.bn.weight), ptr(stats[0]),
              ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), st)
         k = (ysc, ysh, ylo, ptr(coef[2]), ptr(coef[3]), ptr(coef[4]))
         g = new_view(N, ci, H, W, dev)
-        call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st)
+        call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
+             meta=4.0 * N * HW * (2 * co + ci))
         workers = lib.ocrs_det_pw_wgrad_workers(N, H, W)
         wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
         call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
-             ptr(self.dw.weight), ptr(wpart), st)
+             ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
         d_wpw = torch.empty_like(self.pw.weight)
         _finalize(wpart, workers, co * ci, d_wpw, st)
         drows = lib.ocrs_det_dw_bwd_rows(N, H, W)
@@ -117,7 +119,7 @@ class _Sep:
         if dx is None:
             dx = new_view(N, ci, H, W, dev)
         call("ocrs_det_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
-             dx.ss, int(accumulate), ptr(dpart), st)
+             dx.ss, int(accumulate), ptr(dpart), st, meta=4.0 * N * HW * 3 * ci)
         d_wdw = torch.empty_like(self.dw.weight)
         _finalize(dpart, drows, ci * 9, d_wdw, st)
         return [d_wdw, d_wpw, coef[0].clone(), coef[1].clone()], dx

@@ -1,0 +1,67 @@
+"""Step glue on the device: flat parameter/gradient buffers, fused grad-norm + clip + Adam, and the
+data-parallel gradient all-reduce (one NCCL call on the flat bucket).
+
+Mirrors what the reference scripts do per step with ``torch.optim.Adam(model.parameters())``
+(train_detection.py:378, train_rec.py:381-382) and ``clip_grad_norm_(..., 4.0)`` (train_rec.py:148).
+The reference has no multi-GPU path; the all-reduce follows standard DDP semantics (averaged
+gradients, per-replica BatchNorm statistics), SURVEY section 8e.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+
+class FusedAdam:
+    """Adam (+ optional global-norm clipping) over a model whose parameters and gradients are
+    re-homed into two flat fp32 buffers. ``step()`` = [all-reduce] -> norm -> clip+Adam, 3 launches."""
+
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: float | None = None, process_group=None, world_size: int = 1):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("FusedAdam needs CUDA parameters (no CPU path)")
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat_p[o : o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_g[o : o + p.numel()].view_as(p)
+        self.params, self.n = params, total
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.max_grad_norm = max_grad_norm
+        self.group, self.world = process_group, world_size
+        self.t = 0
+        lib = _lib.lib()
+        self.partials = torch.empty(lib.ocrs_optim_blocks(), dtype=torch.float32, device=dev)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.dev = dev
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def step(self):
+        """Returns the (device) gradient-norm tensor when clipping is on, else None."""
+        st = _lib.stream_ptr(self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+        scale = 1.0 / self.world
+        self.t += 1
+        clip = self.max_grad_norm if self.max_grad_norm is not None else -1.0
+        with torch.cuda.device(self.dev):
+            if clip > 0:
+                call("ocrs_grad_norm", ptr(self.flat_g), self.n, scale, ptr(self.partials), ptr(self.norm), st)
+            call("ocrs_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n, self.lr,
+                 self.betas[0], self.betas[1], self.eps, self.t, scale, clip, ptr(self.norm), st)
+        return self.norm if clip > 0 else None

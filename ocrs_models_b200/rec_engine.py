@@ -13,9 +13,17 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
+import os
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 TARGET_BLOCKS = 2 * 148
+# "tc": tcgen05 3xTF32 tensor-core GEMM (csrc/gemm_tc.cu) wherever TMA alignment allows, else the
+# fp32 CUDA-core GEMM (csrc/gemm.cu). OCRS_GEMM=simt forces the latter (A/B testing).
+GEMM_BACKEND = os.environ.get("OCRS_GEMM", "tc")
+# "persist": one cluster-persistent launch per GRU layer and direction pair (csrc/gru_persist.cu);
+# "steps": one launch per time step (csrc/rec.cu), kept for A/B testing.
+GRU_BACKEND = os.environ.get("OCRS_GRU", "persist")
 
 
 def _empty(shape, dev):
@@ -23,9 +31,12 @@ def _empty(shape, dev):
 
 
 def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bias=None, relu=False,
-         accumulate=False, stats=None, split_ok=False):
-    """C[M,N] = op(A) op(B) through ocrs_gemm. A/B are tensors or raw pointers. With `split_ok` the
-    reduction is split over K when the output has too few tiles to fill the GPU."""
+         accumulate=False, stats=None, split_ok=False, exact=False):
+    """C[M,N] = op(A) op(B). A/B are tensors or raw pointers. With `split_ok` the reduction is split
+    over K when the output has too few tiles to fill the GPU. `exact` forces the fp32-FMA kernel:
+    outputs that feed ReLU / max-pool decisions must be accurate to ~1e-6, because a perturbation d
+    of a pre-activation flips a fraction ~d of the gates and moves gradients by ~sqrt(d); the
+    3xTF32 tensor-core path (~1e-5, its fp32 accumulation truncates) is used everywhere else."""
     dev = out.device if out is not None else (A.device if isinstance(A, torch.Tensor) else None)
     pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
     pb = B.data_ptr() if isinstance(B, torch.Tensor) else B
@@ -34,19 +45,22 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bi
     if ldc is None:
         ldc = N
     lib = _lib.lib()
+    tc = GEMM_BACKEND == "tc" and not exact and bool(lib.ocrs_gemm_tc_supported(pa, lda, pb, ldb))
+    fn = "ocrs_gemm_tc" if tc else "ocrs_gemm"
     splits = 1
     if split_ok:
-        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        bn = (32 if N <= 32 else 64 if N <= 64 else 128) if tc else 128
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
         want = max(1, min(TARGET_BLOCKS // tiles, K // 256))
-        splits = lib.ocrs_gemm_splits(K, want)
+        splits = (lib.ocrs_gemm_tc_splits if tc else lib.ocrs_gemm_splits)(K, want)
     if splits == 1:
-        call("ocrs_gemm", pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(out), ldc, M, N, K, ptr(bias),
-             int(relu), int(accumulate), ptr(stats), 1, st)
+        call(fn, pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(out), ldc, M, N, K, ptr(bias),
+             int(relu), int(accumulate), ptr(stats), 1, st, meta=2.0 * M * N * K)
     else:
         assert ldc == N and bias is None and not relu and not accumulate and stats is None
         part = _empty((splits, M, N), out.device)
-        call("ocrs_gemm", pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(part), N, M, N, K, None, 0, 0, None,
-             splits, st)
+        call(fn, pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(part), N, M, N, K, None, 0, 0, None,
+             splits, st, meta=2.0 * M * N * K)
         call("ocrs_finalize_partials", ptr(part), splits, M * N, ptr(out), st)
     return out
 
@@ -142,7 +156,7 @@ class _RecFunction(torch.autograd.Function):
                 rows = lib.ocrs_gemm_stat_rows(M)
                 stats = _empty((rows, 2, cout), dev) if training else None
                 y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1], st,
-                         stats=stats)
+                         stats=stats, exact=True)
                 bs = _bn_finalize(bn, stats, rows, M, training, relu, st, dev)
                 Hp, Wp = Ho // ph, Wo // pw
                 if out is None:
@@ -157,7 +171,7 @@ class _RecFunction(torch.autograd.Function):
                 col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, 3, 3, 1, 1, st)
                 M = N * Ho * Wo
                 a = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, conv.out_channels,
-                         col.shape[1], st, bias=conv.bias, relu=True)
+                         col.shape[1], st, bias=conv.bias, relu=True, exact=True)
                 return a, dict(col=col, a=a, inp_geom=(Hh, Ww, cin))
 
             a3, H3, W3, rec["3"] = conv_bn_pool(a0, H1, W1, 32, cv["3"], cv["4"], 2, 2, 0, True)
@@ -186,7 +200,8 @@ class _RecFunction(torch.autograd.Function):
                     gi.append(gemm(layer_in, isz, True, w_ih, isz, True, TN, 768, isz, st, bias=b_ih))
                 out = _empty((T, N, 512), dev)
                 gates = _empty((T, N, 2, 4, 256), dev)
-                call("ocrs_gru_layer_fwd", ptr(gi[0]), ptr(gi[1]), ptr(getattr(gru, f"weight_hh_l{layer}")),
+                call("ocrs_gru_layer_fwd_persist" if GRU_BACKEND == "persist" else "ocrs_gru_layer_fwd",
+                     ptr(gi[0]), ptr(gi[1]), ptr(getattr(gru, f"weight_hh_l{layer}")),
                      ptr(getattr(gru, f"weight_hh_l{layer}_reverse")), ptr(getattr(gru, f"bias_hh_l{layer}")),
                      ptr(getattr(gru, f"bias_hh_l{layer}_reverse")), ptr(out), ptr(gates), T, N, st)
                 gru_rec.append(dict(x=layer_in, out=out, gates=gates, isz=isz))
@@ -233,9 +248,13 @@ class _RecFunction(torch.autograd.Function):
                     whhT.append(t_)
                 dgi = [_empty((TN, 768), dev) for _ in range(2)]
                 dgh = [_empty((TN, 768), dev) for _ in range(2)]
-                carry = _empty((2, N, 256), dev)
-                call("ocrs_gru_layer_bwd", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates), ptr(dgi[0]),
-                     ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), ptr(carry), T, N, st)
+                if GRU_BACKEND == "persist":
+                    call("ocrs_gru_layer_bwd_persist", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates),
+                         ptr(dgi[0]), ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), T, N, st)
+                else:
+                    carry = _empty((2, N, 256), dev)
+                    call("ocrs_gru_layer_bwd", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates),
+                         ptr(dgi[0]), ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), ptr(carry), T, N, st)
                 d_in = _empty((TN, isz), dev)
                 for d, nm in enumerate(names):
                     w_ih = getattr(gru, "weight_ih_" + nm)
