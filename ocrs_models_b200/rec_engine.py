@@ -24,6 +24,8 @@ GEMM_BACKEND = os.environ.get("OCRS_GEMM", "tc")
 # "persist": one cluster-persistent launch per GRU layer and direction pair (csrc/gru_persist.cu);
 # "steps": one launch per time step (csrc/rec.cu), kept for A/B testing.
 GRU_BACKEND = os.environ.get("OCRS_GRU", "persist")
+# OCRS_EXACT_FWD=1 runs the forward convolutions on the fp32-FMA GEMM instead of the tensor cores.
+EXACT_FWD = os.environ.get("OCRS_EXACT_FWD", "0") == "1"
 
 
 def _empty(shape, dev):
@@ -35,8 +37,8 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bi
     """C[M,N] = op(A) op(B). A/B are tensors or raw pointers. With `split_ok` the reduction is split
     over K when the output has too few tiles to fill the GPU. `exact` forces the fp32-FMA kernel:
     outputs that feed ReLU / max-pool decisions must be accurate to ~1e-6, because a perturbation d
-    of a pre-activation flips a fraction ~d of the gates and moves gradients by ~sqrt(d); the
-    3xTF32 tensor-core path (~1e-5, its fp32 accumulation truncates) is used everywhere else."""
+    of a pre-activation flips a fraction ~d of the gates and moves gradients by ~sqrt(d). Kept as
+    an A/B switch: the 4-accumulator 3xTF32 tensor-core kernel reaches the same accuracy."""
     dev = out.device if out is not None else (A.device if isinstance(A, torch.Tensor) else None)
     pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
     pb = B.data_ptr() if isinstance(B, torch.Tensor) else B
@@ -156,7 +158,7 @@ class _RecFunction(torch.autograd.Function):
                 rows = lib.ocrs_gemm_stat_rows(M)
                 stats = _empty((rows, 2, cout), dev) if training else None
                 y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1], st,
-                         stats=stats, exact=True)
+                         stats=stats, exact=EXACT_FWD)
                 bs = _bn_finalize(bn, stats, rows, M, training, relu, st, dev)
                 Hp, Wp = Ho // ph, Wo // pw
                 if out is None:
@@ -171,7 +173,7 @@ class _RecFunction(torch.autograd.Function):
                 col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, 3, 3, 1, 1, st)
                 M = N * Ho * Wo
                 a = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, conv.out_channels,
-                         col.shape[1], st, bias=conv.bias, relu=True, exact=True)
+                         col.shape[1], st, bias=conv.bias, relu=True, exact=EXACT_FWD)
                 return a, dict(col=col, a=a, inp_geom=(Hh, Ww, cin))
 
             a3, H3, W3, rec["3"] = conv_bn_pool(a0, H1, W1, 32, cv["3"], cv["4"], 2, 2, 0, True)
