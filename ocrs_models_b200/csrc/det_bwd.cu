@@ -11,17 +11,27 @@
 // patch; per-block partial results are reduced in double by finalize_partials (deterministic).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-__global__ void finalize_partials_kernel(const float* __restrict__ partials, int nblk, int K,
-                                         float* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+__global__ void __launch_bounds__(256)
+finalize_partials_kernel(const float* __restrict__ partials, int nblk, int K, float* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int kx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partials[(size_t)b * K + k];
-  out[k] = (float)s;
+  if (k < K)
+    for (int b = ry; b < nblk; b += 8) s += (double)partials[(size_t)b * K + k];
+  red[ry][kx] = s;
+  __syncthreads();
+  if (ry == 0 && k < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][kx];
+    out[k] = (float)t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,22 +272,48 @@ pw_wgrad_kernel(const float* __restrict__ d_a, long long da_ss, const float* __r
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  __shared__ float skc[6][16];
+  __shared__ float swd[16][9];
+  __shared__ float sxf[3][16];
+  if (tid >= 32 && tid < 48 && isc) {
+    const int c = tid - 32;
+    const bool v = c < nci;
+    sxf[0][c] = v ? isc[ci0 + c] : 1.f; sxf[1][c] = v ? ish[ci0 + c] : 0.f; sxf[2][c] = v ? ilo[ci0 + c] : -INFINITY;
+  }
+  if (tid < 16) {
+    const bool v = tid < nco;
+    skc[0][tid] = v ? k.sc[co0 + tid] : 0.f; skc[1][tid] = v ? k.sh[co0 + tid] : 0.f;
+    skc[2][tid] = v ? k.lo[co0 + tid] : 0.f; skc[3][tid] = v ? k.k1[co0 + tid] : 0.f;
+    skc[4][tid] = v ? k.k2[co0 + tid] : 0.f; skc[5][tid] = v ? k.k3[co0 + tid] : 0.f;
+  }
+  if (tid < 144) swd[tid / 9][tid % 9] = (tid / 9 < nci) ? wdw[(size_t)(ci0 + tid / 9) * 9 + tid % 9] : 0.f;
   const int tiles = tiles_x * tiles_y;
   const long long total = (long long)N * tiles;
   for (long long work = blockIdx.x; work < total; work += gridDim.x) {
     const int n = (int)(work / tiles), tile = (int)(work % tiles);
     const int x0 = (tile % tiles_x) * WG_TW, y0 = (tile / tiles_x) * WG_TH;
     __syncthreads();
-    for (int i = tid; i < nci * WG_SPLANE; i += 256) {
-      const int c = i / WG_SPLANE, r = i - c * WG_SPLANE;
-      const int ry = r / WG_SROW, rx = r - ry * WG_SROW;
-      const int gy = y0 + ry - 1, gx = x0 + rx - 1;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = x[(size_t)n * x_ss + (size_t)(ci0 + c) * HW + (size_t)gy * W + gx];
-        if (isc) v = xform_apply(v, isc[ci0 + c], ish[ci0 + c], ilo[ci0 + c]);
+    {
+      constexpr int NSLOT = (WG_SPLANE + 255) / 256;
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int pos = tid + 256 * sl;
+        if (pos < WG_SPLANE) {
+          const int ry = pos / WG_SROW, rx = pos - ry * WG_SROW;
+          const int gy = y0 + ry - 1, gx = x0 + rx - 1;
+          const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+          const float* src = x + (size_t)n * x_ss + (size_t)ci0 * HW + (size_t)(in ? gy * W + gx : 0);
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = (in && c < nci) ? src[(size_t)c * HW] : 0.f;
+          if (isc && in) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) if (c < nci) v[c] = xform_apply(v[c], sxf[0][c], sxf[1][c], sxf[2][c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) xs[c * WG_SPLANE + pos] = v[c];
+        }
       }
-      xs[i] = v;
     }
     // dy for this thread's pixel
     const int gy = y0 + ty, gx = x0 + tx;
@@ -288,8 +324,8 @@ pw_wgrad_kernel(const float* __restrict__ d_a, long long da_ss, const float* __r
       float v = 0.f;
       if (ok && o < nco) {
         const size_t off = (size_t)(co0 + o) * HW + (size_t)gy * W + gx;
-        v = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], k.sc[co0 + o],
-                  k.sh[co0 + o], k.lo[co0 + o], k.k1[co0 + o], k.k2[co0 + o], k.k3[co0 + o]);
+        v = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], skc[0][o], skc[1][o], skc[2][o],
+                  skc[3][o], skc[4][o], skc[5][o]);
       }
       va[o] = v;
     }
@@ -304,11 +340,10 @@ pw_wgrad_kernel(const float* __restrict__ d_a, long long da_ss, const float* __r
       float s = 0.f;
       if (ok && c < nci) {
         const float* t = xs + c * WG_SPLANE + ty * WG_SROW + tx;
-        const float* wk = wdw + (size_t)(ci0 + c) * 9;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) s = fmaf(t[ky * WG_SROW + kx], __ldg(wk + ky * 3 + kx), s);
+          for (int kx = 0; kx < 3; ++kx) s = fmaf(t[ky * WG_SROW + kx], swd[c][ky * 3 + kx], s);
       }
       vb[c] = s;
     }
@@ -327,6 +362,161 @@ pw_wgrad_kernel(const float* __restrict__ d_a, long long da_ss, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor-core version of pw_wgrad. The reduction dW[co][ci] = sum_p dy[co][p] * dwout[ci][p] has
+// M = N = 16 per block and K = pixels: far too skinny for tcgen05 (M >= 64, operands from shared
+// memory), but a perfect fit for warp-level mma.sync.m16n8k8 (TF32) fed straight from registers:
+// lane (g, t) of a warp owns pixels {t, t+4} of each 8-pixel k-step for channels {g, g+8}, which
+// is exactly the A (dy) and B (dwout) fragment layout, so nothing is staged or transposed.
+// fp32-class accuracy through the 3xTF32 split (hi.hi + hi.lo + lo.hi); the fragment accumulators
+// are flushed into fp32 registers after every tile so the tensor core's truncating accumulation
+// never sees chains longer than 12 products.
+__device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 3)
+pw_wgrad_mma_kernel(const float* __restrict__ d_a, long long da_ss, const float* __restrict__ y,
+                    long long y_ss, int Cout, DyCoef k, const float* __restrict__ x, long long x_ss,
+                    int Cin, int H, int W, const float* __restrict__ isc, const float* __restrict__ ish,
+                    const float* __restrict__ ilo, const float* __restrict__ wdw, int N, int tiles_x,
+                    int tiles_y, float* __restrict__ partials) {
+  __shared__ float xs[16 * WG_SPLANE];
+  __shared__ float sred[8][256];
+  __shared__ float sxf[3][16];
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cit = (Cin + 15) / 16;
+  const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
+  const int nco = min(16, Cout - co0), nci = min(16, Cin - ci0);
+  const size_t HW = (size_t)H * W;
+  if (tid < 16) {
+    const bool v = tid < nci && isc != nullptr;
+    sxf[0][tid] = v ? isc[ci0 + tid] : 1.f; sxf[1][tid] = v ? ish[ci0 + tid] : 0.f; sxf[2][tid] = v ? ilo[ci0 + tid] : -INFINITY;
+  }
+  // per-lane constants for its two output channels (g, g+8) and two input channels (g, g+8)
+  float ksc[2], ksh[2], klo[2], kk1[2], kk2[2], kk3[2], wd[2][9];
+  bool cov[2], civ[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int o = g + 8 * h;
+    cov[h] = o < nco;
+    civ[h] = o < nci;
+    ksc[h] = cov[h] ? k.sc[co0 + o] : 0.f; ksh[h] = cov[h] ? k.sh[co0 + o] : 0.f; klo[h] = cov[h] ? k.lo[co0 + o] : 0.f;
+    kk1[h] = cov[h] ? k.k1[co0 + o] : 0.f; kk2[h] = cov[h] ? k.k2[co0 + o] : 0.f; kk3[h] = cov[h] ? k.k3[co0 + o] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wd[h][q] = civ[h] ? wdw[(size_t)(ci0 + o) * 9 + q] : 0.f;
+  }
+  float ctot[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ctot[j][q] = 0.f;
+  const int tiles = tiles_x * tiles_y;
+  const long long total = (long long)N * tiles;
+  for (long long work = blockIdx.x; work < total; work += gridDim.x) {
+    const int n = (int)(work / tiles), tile = (int)(work % tiles);
+    const int x0 = (tile % tiles_x) * WG_TW, y0 = (tile / tiles_x) * WG_TH;
+    __syncthreads();
+    {
+      constexpr int NSLOT = (WG_SPLANE + 255) / 256;
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int pos = tid + 256 * sl;
+        if (pos < WG_SPLANE) {
+          const int ry = pos / WG_SROW, rx = pos - ry * WG_SROW;
+          const int gy = y0 + ry - 1, gx = x0 + rx - 1;
+          const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+          const float* src = x + (size_t)n * x_ss + (size_t)ci0 * HW + (size_t)(in ? gy * W + gx : 0);
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = (in && c < nci) ? src[(size_t)c * HW] : 0.f;
+          if (in) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = xform_apply(v[c], sxf[0][c], sxf[1][c], sxf[2][c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) xs[c * WG_SPLANE + pos] = (in && c < nci) ? v[c] : 0.f;
+        }
+      }
+    }
+    // dy fragments of the whole tile row (4 k-steps x {t, t+4} x {g, g+8}) : issue all loads first
+    const int gy = y0 + ty;
+    float dyv[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int h = q & 1, px = x0 + ks * 8 + t + 4 * (q >> 1);
+        float v = 0.f;
+        if (cov[h] && gy < H && px < W) {
+          const size_t off = (size_t)(co0 + g + 8 * h) * HW + (size_t)gy * W + px;
+          v = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], ksc[h], ksh[h], klo[h], kk1[h], kk2[h], kk3[h]);
+        }
+        dyv[ks][q] = v;  // q: 0 = (g, t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
+      }
+    __syncthreads();
+    float c[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[j][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tf32_split(dyv[ks][q], ah[q], al[q]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        // dwout[ci = 8j + g][pixel t / t+4] : depthwise stencil from the shared tile
+        float b[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int lx = ks * 8 + t + 4 * e;
+          const float* tp = xs + (8 * j + g) * WG_SPLANE + ty * WG_SROW + lx;
+          float sacc = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) sacc = fmaf(tp[ky * WG_SROW + kx], wd[j][ky * 3 + kx], sacc);
+          b[e] = (gy < H && x0 + lx < W) ? sacc : 0.f;
+        }
+        uint32_t bh0, bl0, bh1, bl1;
+        tf32_split(b[0], bh0, bl0);
+        tf32_split(b[1], bh1, bl1);
+        mma_tf32(c[j], al, bh0, bh1);
+        mma_tf32(c[j], ah, bl0, bl1);
+        mma_tf32(c[j], ah, bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ctot[j][q] += c[j][q];
+  }
+  // C fragment -> (co, ci): c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1), n-tile j adds 8 to ci
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    sred[ty][(g) * 16 + 8 * j + 2 * t] = ctot[j][0];
+    sred[ty][(g) * 16 + 8 * j + 2 * t + 1] = ctot[j][1];
+    sred[ty][(g + 8) * 16 + 8 * j + 2 * t] = ctot[j][2];
+    sred[ty][(g + 8) * 16 + 8 * j + 2 * t + 1] = ctot[j][3];
+  }
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += sred[w][tid];
+  const int o = tid >> 4, ci = tid & 15;
+  if (o < nco && ci < nci) partials[((size_t)blockIdx.x * Cout + co0 + o) * Cin + ci0 + ci] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Depthwise 3x3 backward for one channel plane tile: d_x = corr(g, flip(w)); dW[k] partials.
 constexpr int DW_TH = 32;
 __global__ void __launch_bounds__(256)
@@ -334,19 +524,28 @@ dw_bwd_kernel(const float* __restrict__ g, long long g_ss, const float* __restri
               long long x_ss, int C, int H, int W, const float* __restrict__ isc,
               const float* __restrict__ ish, const float* __restrict__ ilo,
               const float* __restrict__ wdw, float* __restrict__ dx, long long dx_ss,
-              int accumulate, float* __restrict__ partials, int tiles_x) {
+              int accumulate, float* __restrict__ partials, int tiles_x, int tiles) {
   __shared__ float gs[(DW_TH + 2) * 34];
   __shared__ float xs[(DW_TH + 2) * 34];
   __shared__ float red[8][9];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int tile = blockIdx.x, c = blockIdx.y, n = blockIdx.z;
-  const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * DW_TH;
+  const int c = blockIdx.y, n = blockIdx.z;
   const size_t HW = (size_t)H * W;
   const float* gp = g + (size_t)n * g_ss + (size_t)c * HW;
   const float* xp = x + (size_t)n * x_ss + (size_t)c * HW;
   const bool need_x = partials != nullptr;
   float s = 1.f, t = 0.f, l = -INFINITY;
   if (isc) { s = isc[c]; t = ish[c]; l = ilo[c]; }
+  float w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = wdw[(size_t)c * 9 + k];
+  float dw[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dw[k] = 0.f;
+  float* dxp = dx + (size_t)n * dx_ss + (size_t)c * HW;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * DW_TH;
+  __syncthreads();
   for (int i = tid; i < (DW_TH + 2) * 34; i += 256) {
     const int ry = i / 34, rx = i - ry * 34;
     const int gy = y0 + ry - 1, gx = x0 + rx - 1;
@@ -361,14 +560,7 @@ dw_bwd_kernel(const float* __restrict__ g, long long g_ss, const float* __restri
     gs[i] = gv;
     xs[i] = xv;
   }
-  float w[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) w[k] = wdw[(size_t)c * 9 + k];
   __syncthreads();
-  float dw[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) dw[k] = 0.f;
-  float* dxp = dx + (size_t)n * dx_ss + (size_t)c * HW;
 #pragma unroll
   for (int p = 0; p < DW_TH / 8; ++p) {
     const int ly = ty * (DW_TH / 8) + p, gy = y0 + ly, gx = x0 + tx;
@@ -389,6 +581,7 @@ dw_bwd_kernel(const float* __restrict__ g, long long g_ss, const float* __restri
       }
     }
   }
+  }  // tile loop
   if (!need_x) return;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -400,7 +593,7 @@ dw_bwd_kernel(const float* __restrict__ g, long long g_ss, const float* __restri
     float v = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v += red[q][tid];
-    const size_t blk = (size_t)n * gridDim.x + tile;
+    const size_t blk = (size_t)n * gridDim.x + blockIdx.x;
     partials[(blk * C + c) * 9 + tid] = v;
   }
 }
@@ -569,7 +762,7 @@ plane_sum_kernel(const float* __restrict__ v, long long v_ss, int C, long long H
 extern "C" {
 
 int ocrs_finalize_partials(const float* partials, int nblk, int K, float* out, void* stream) {
-  finalize_partials_kernel<<<ocrs_cdiv(K, 128), 128, 0, (cudaStream_t)stream>>>(partials, nblk, K, out);
+  finalize_partials_kernel<<<ocrs_cdiv(K, 32), 256, 0, (cudaStream_t)stream>>>(partials, nblk, K, out);
   OCRS_CHECK_LAUNCH("finalize_partials_kernel");
   return 0;
 }
@@ -638,7 +831,7 @@ int ocrs_det_pwT_bwd(const float* d_a, long long da_ss, const float* y, long lon
 
 int ocrs_det_pw_wgrad_workers(int N, int H, int W) {
   const long long tiles = (long long)N * ocrs_cdiv(W, WG_TW) * ocrs_cdiv(H, WG_TH);
-  return (int)(tiles < 2 * OCRS_NUM_SMS ? tiles : 2 * OCRS_NUM_SMS);
+  return (int)(tiles < 3 * OCRS_NUM_SMS ? tiles : 3 * OCRS_NUM_SMS);
 }
 // partials: [workers][Cout][Cin]; must be zero-filled when Cout or Cin is not a multiple of 16? no:
 // every (co, ci) element is written by exactly one block column.
@@ -656,22 +849,30 @@ int ocrs_det_pw_wgrad(const float* d_a, long long da_ss, const float* y, long lo
   DyCoef k{sc, sh, lo, k1, k2, k3};
   const int tiles_x = ocrs_cdiv(W, WG_TW), tiles_y = ocrs_cdiv(H, WG_TH);
   dim3 grid(ocrs_det_pw_wgrad_workers(N, H, W), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
-  pw_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin,
-                                                            H, W, isc, ish, ilo, wdw, N, tiles_x,
-                                                            tiles_y, partials);
+  if (getenv("OCRS_PW_WGRAD_SIMT"))
+    pw_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin, H, W, isc,
+                                                              ish, ilo, wdw, N, tiles_x, tiles_y, partials);
+  else
+    pw_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin, H, W, isc,
+                                                               ish, ilo, wdw, N, tiles_x, tiles_y, partials);
   OCRS_CHECK_LAUNCH("pw_wgrad_kernel");
   return 0;
 }
 
-int ocrs_det_dw_bwd_rows(int N, int H, int W) { return N * ocrs_cdiv(W, 32) * ocrs_cdiv(H, DW_TH); }
+constexpr int DW_MAX_BLOCKS_X = 16;
+int ocrs_det_dw_bwd_rows(int N, int H, int W) {
+  const int tiles = ocrs_cdiv(W, 32) * ocrs_cdiv(H, DW_TH);
+  return N * (tiles < DW_MAX_BLOCKS_X ? tiles : DW_MAX_BLOCKS_X);
+}
 // partials: [rows][C][9] or NULL to skip the weight gradient (and the read of x).
 int ocrs_det_dw_bwd(const float* g, long long g_ss, const float* x, long long x_ss, int N, int C, int H,
                     int W, const float* isc, const float* ish, const float* ilo, const float* wdw,
                     float* dx, long long dx_ss, int accumulate, float* partials, void* stream) {
   const int tiles_x = ocrs_cdiv(W, 32), tiles_y = ocrs_cdiv(H, DW_TH);
-  dim3 grid(tiles_x * tiles_y, C, N);
+  const int tiles = tiles_x * tiles_y;
+  dim3 grid(tiles < DW_MAX_BLOCKS_X ? tiles : DW_MAX_BLOCKS_X, C, N);
   dw_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, g_ss, x, x_ss, C, H, W, isc, ish, ilo, wdw, dx,
-                                                        dx_ss, accumulate, partials, tiles_x);
+                                                        dx_ss, accumulate, partials, tiles_x, tiles);
   OCRS_CHECK_LAUNCH("dw_bwd_kernel");
   return 0;
 }

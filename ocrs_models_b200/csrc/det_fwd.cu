@@ -43,19 +43,37 @@ dwpw_fwd_kernel(const float* __restrict__ x, long long x_ss, int Cin, int H, int
 #pragma unroll
     for (int o = 0; o < CO_T; ++o) acc[p][o] = 0.f;
 
+  // Per-thread tile slots: position (ry, rx) of the haloed tile, fixed for every channel, so the
+  // per-element address arithmetic is done once per tile and the loads of a chunk are issued as
+  // independent batches (memory-level parallelism instead of a dependent load->store chain).
+  constexpr int NSLOT = (SPLANE + 255) / 256;
+  int goff[NSLOT];
+#pragma unroll
+  for (int sl = 0; sl < NSLOT; ++sl) {
+    const int pos = tid + 256 * sl;
+    const int ry = pos / SROW, rx = pos - ry * SROW;
+    const int gy = y0 + ry - 1, gx = x0 + rx - 1;
+    goff[sl] = (pos < SPLANE && gy >= 0 && gy < H && gx >= 0 && gx < W) ? gy * W + gx : -1;
+  }
   for (int ci0 = 0; ci0 < Cin; ci0 += CI_CHUNK) {
     const int nci = min(CI_CHUNK, Cin - ci0);
     __syncthreads();
-    for (int i = tid; i < nci * SPLANE; i += 256) {
-      const int c = i / SPLANE, r = i - c * SPLANE;
-      const int ry = r / SROW, rx = r - ry * SROW;
-      const int gy = y0 + ry - 1, gx = x0 + rx - 1;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = xn[(size_t)(ci0 + c) * HW + (size_t)gy * W + gx];
-        if (in_scale) v = xform_apply(v, in_scale[ci0 + c], in_shift[ci0 + c], in_lo[ci0 + c]);
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      const int pos = tid + 256 * sl;
+      if (pos < SPLANE) {
+        float v[CI_CHUNK];
+#pragma unroll
+        for (int c = 0; c < CI_CHUNK; ++c)
+          v[c] = (c < nci && goff[sl] >= 0) ? xn[(size_t)(ci0 + c) * HW + goff[sl]] : 0.f;
+        if (in_scale && goff[sl] >= 0) {
+#pragma unroll
+          for (int c = 0; c < CI_CHUNK; ++c)
+            if (c < nci) v[c] = xform_apply(v[c], in_scale[ci0 + c], in_shift[ci0 + c], in_lo[ci0 + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CI_CHUNK; ++c) xs[c * SPLANE + pos] = v[c];
       }
-      xs[i] = v;
     }
     for (int i = tid; i < nci * 9; i += 256) sdw[i] = wdw[(size_t)ci0 * 9 + i];
     for (int i = tid; i < nci * CO_T; i += 256) {
