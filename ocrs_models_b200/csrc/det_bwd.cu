@@ -833,8 +833,7 @@ int ocrs_det_pw_wgrad_workers(int N, int H, int W) {
   const long long tiles = (long long)N * ocrs_cdiv(W, WG_TW) * ocrs_cdiv(H, WG_TH);
   return (int)(tiles < 3 * OCRS_NUM_SMS ? tiles : 3 * OCRS_NUM_SMS);
 }
-// partials: [workers][Cout][Cin]; must be zero-filled when Cout or Cin is not a multiple of 16? no:
-// every (co, ci) element is written by exactly one block column.
+// partials: [workers][Cout][Cin], fully written (every (co, ci) belongs to exactly one block column).
 int ocrs_det_pw_wgrad(const float* d_a, long long da_ss, const float* y, long long y_ss, int N,
                       int Cout, int H, int W, const float* sc, const float* sh, const float* lo,
                       const float* k1, const float* k2, const float* k3, const float* x,

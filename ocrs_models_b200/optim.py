@@ -14,6 +14,20 @@ from . import _lib
 from ._lib import call, ptr
 
 
+def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """The one data-path collective of the DDP step: sum the flat gradient bucket over the ranks in
+    place (NCCL over NVLink on GPUs; gloo in the CPU tests). The 1/world averaging is folded into the
+    clip/Adam kernels as `grad_scale`, so no extra pass touches the bucket."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=group)
+    return flat
+
+
+def shard_seed(base_seed: int, rank: int) -> int:
+    """Per-rank data seed (generator seed 1234 + rank); weights use the un-offset seed."""
+    return base_seed + rank
+
+
 class FusedAdam:
     """Adam (+ optional global-norm clipping) over a model whose parameters and gradients are
     re-homed into two flat fp32 buffers. ``step()`` = [all-reduce] -> norm -> clip+Adam, 3 launches."""
@@ -55,7 +69,7 @@ class FusedAdam:
         """Returns the (device) gradient-norm tensor when clipping is on, else None."""
         st = _lib.stream_ptr(self.dev)
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.group)
+            allreduce_sum_(self.flat_g, self.group)
         scale = 1.0 / self.world
         self.t += 1
         clip = self.max_grad_norm if self.max_grad_norm is not None else -1.0
