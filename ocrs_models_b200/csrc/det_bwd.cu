@@ -546,19 +546,24 @@ dw_bwd_kernel(const float* __restrict__ g, long long g_ss, const float* __restri
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
   const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * DW_TH;
   __syncthreads();
-  for (int i = tid; i < (DW_TH + 2) * 34; i += 256) {
-    const int ry = i / 34, rx = i - ry * 34;
-    const int gy = y0 + ry - 1, gx = x0 + rx - 1;
-    float gv = 0.f, xv = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      gv = gp[(size_t)gy * W + gx];
-      if (need_x) {
-        xv = xp[(size_t)gy * W + gx];
-        if (isc) xv = xform_apply(xv, s, t, l);
-      }
+  {
+    constexpr int NPOS = (DW_TH + 2) * 34, NSLOT = (NPOS + 255) / 256;
+    float gv[NSLOT], xv[NSLOT];
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      const int i = tid + 256 * sl;
+      const int ry = i / 34, rx = i - ry * 34;
+      const int gy = y0 + ry - 1, gx = x0 + rx - 1;
+      const bool in = i < NPOS && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      gv[sl] = in ? gp[(size_t)gy * W + gx] : 0.f;
+      xv[sl] = (in && need_x) ? xp[(size_t)gy * W + gx] : 0.f;
+      if (in && need_x && isc) xv[sl] = xform_apply(xv[sl], s, t, l);
     }
-    gs[i] = gv;
-    xs[i] = xv;
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      const int i = tid + 256 * sl;
+      if (i < NPOS) { gs[i] = gv[sl]; xs[i] = xv[sl]; }
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -605,15 +610,24 @@ __global__ void pool2_bwd_kernel(const float* __restrict__ x, long long x_ss, in
                                  const float* __restrict__ sc, const float* __restrict__ sh,
                                  const float* __restrict__ lo, const float* __restrict__ dout,
                                  long long dout_ss, float* __restrict__ din, long long din_ss) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  // thread = one 2x2 cell (cy, cx) of the full-resolution plane, including partial cells of an odd edge
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cy = blockIdx.y * blockDim.y + threadIdx.y;
   const int c = blockIdx.z % C, n = blockIdx.z / C;
+  const int iy = 2 * cy, ix = 2 * cx;
   if (ix >= W || iy >= H) return;
-  const int Ho = H / 2, Wo = W / 2, oy = iy >> 1, ox = ix >> 1;
-  float r = 0.f;
-  if (oy < Ho && ox < Wo) {
-    const float* p = x + (size_t)n * x_ss + (size_t)c * H * W + (size_t)(2 * oy) * W + 2 * ox;
-    float v[4] = {p[0], p[1], p[W], p[W + 1]};
+  const int Ho = H / 2, Wo = W / 2;
+  float* dp = din + (size_t)n * din_ss + (size_t)c * H * W + (size_t)iy * W + ix;
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cy < Ho && cx < Wo) {
+    const float* p = x + (size_t)n * x_ss + (size_t)c * H * W + (size_t)iy * W + ix;
+    float v[4];
+    if ((W & 1) == 0 && (((uintptr_t)p) & 7) == 0) {
+      const float2 a = *reinterpret_cast<const float2*>(p), b = *reinterpret_cast<const float2*>(p + W);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+      v[0] = p[0]; v[1] = p[1]; v[2] = p[W]; v[3] = p[W + 1];
+    }
     if (sc) {
       const float s = sc[c], t = sh[c], l = lo[c];
 #pragma unroll
@@ -624,10 +638,19 @@ __global__ void pool2_bwd_kernel(const float* __restrict__ x, long long x_ss, in
 #pragma unroll
     for (int q = 1; q < 4; ++q)
       if (v[q] > m || isnan(v[q])) { m = v[q]; am = q; }
-    if (am == (iy & 1) * 2 + (ix & 1))
-      r = dout[(size_t)n * dout_ss + (size_t)c * Ho * Wo + (size_t)oy * Wo + ox];
+    const float gv = dout[(size_t)n * dout_ss + (size_t)c * Ho * Wo + (size_t)cy * Wo + cx];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = (q == am) ? gv : 0.f;
   }
-  din[(size_t)n * din_ss + (size_t)c * H * W + (size_t)iy * W + ix] = r;
+  const bool x1 = ix + 1 < W, y1 = iy + 1 < H;
+  if (x1 && (W & 1) == 0 && (((uintptr_t)dp) & 7) == 0) {
+    *reinterpret_cast<float2*>(dp) = make_float2(r[0], r[1]);
+    if (y1) *reinterpret_cast<float2*>(dp + W) = make_float2(r[2], r[3]);
+  } else {
+    dp[0] = r[0];
+    if (x1) dp[1] = r[1];
+    if (y1) { dp[W] = r[2]; if (x1) dp[W + 1] = r[3]; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -741,6 +764,108 @@ convt_wgrad_kernel(const float* __restrict__ x, long long x_ss, int Cin, int Hin
   const int c = tid >> 4, j = tid & 15;
   // partial layout [worker][Cin][Cout*9] == weight layout [Cin][Cout][3][3]
   if (c < nci && j < nb) partials[((size_t)blockIdx.x * Cin + ci0 + c) * CK + b0 + j] = s;
+}
+
+// Tensor-core version (same fragment trick as pw_wgrad_mma_kernel): rows a = 16 input channels,
+// columns b = 16 of the Cout*9 (co, tap) pairs, K = input pixels; operands gathered from global
+// memory directly in mma.sync fragment layout, 3xTF32, accumulators flushed every 4 k-steps.
+__global__ void __launch_bounds__(256)
+convt_wgrad_mma_kernel(const float* __restrict__ x, long long x_ss, int Cin, int Hin, int Win,
+                       const float* __restrict__ isc, const float* __restrict__ ish,
+                       const float* __restrict__ ilo, const float* __restrict__ dout, long long dout_ss,
+                       int Cout, int Hs, int Ws, int N, float* __restrict__ partials) {
+  __shared__ float sred[8][256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int CK = Cout * 9;
+  const int bt = (CK + 15) / 16;
+  const int ci0 = (blockIdx.y / bt) * 16, b0 = (blockIdx.y % bt) * 16;
+  const int nci = min(16, Cin - ci0), nb = min(16, CK - b0);
+  const size_t HWi = (size_t)Hin * Win, HWs = (size_t)Hs * Ws;
+  const long long total = (long long)N * HWi;
+  float sc[2], sh[2], lo[2];
+  bool civ[2];
+  int bco[2], bky[2], bkx[2];
+  bool bv[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = g + 8 * h;
+    civ[h] = c < nci;
+    sc[h] = (civ[h] && isc) ? isc[ci0 + c] : 1.f;
+    sh[h] = (civ[h] && isc) ? ish[ci0 + c] : 0.f;
+    lo[h] = (civ[h] && isc) ? ilo[ci0 + c] : -INFINITY;
+    const int j = b0 + 8 * h + g;  // this lane's B row for n-tile h
+    bv[h] = 8 * h + g < nb;
+    bco[h] = bv[h] ? j / 9 : 0;
+    const int kk = bv[h] ? j - bco[h] * 9 : 0;
+    bky[h] = kk / 3;
+    bkx[h] = kk - bky[h] * 3;
+  }
+  float ctot[2][4], c[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ctot[j][q] = 0.f; c[j][q] = 0.f; }
+  int since_flush = 0;
+  const long long stride = (long long)gridDim.x * 8 * 8;
+  for (long long base = ((long long)blockIdx.x * 8 + wid) * 8; base < total; base += stride) {
+    // this lane's two pixels of the 8-pixel k-step
+    float av[4];
+    float bvv[2][2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const long long pidx = base + t + 4 * e;
+      const bool ok = pidx < total;
+      const int n = ok ? (int)(pidx / (long long)HWi) : 0;
+      const int rem = ok ? (int)(pidx - (long long)n * (long long)HWi) : 0;
+      const int iy = rem / Win, ix = rem - iy * Win;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = 0.f;
+        if (ok && civ[h]) v = xform_apply(x[(size_t)n * x_ss + (size_t)(ci0 + g + 8 * h) * HWi + rem], sc[h], sh[h], lo[h]);
+        av[h + 2 * e] = v;  // 0 = (g, t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
+        float w = 0.f;
+        const int oy = 2 * iy + bky[h], ox = 2 * ix + bkx[h];
+        if (ok && bv[h] && oy < Hs && ox < Ws) w = dout[(size_t)n * dout_ss + (size_t)bco[h] * HWs + (size_t)oy * Ws + ox];
+        bvv[h][e] = w;
+      }
+    }
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tf32_split(av[q], ah[q], al[q]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t bh0, bl0, bh1, bl1;
+      tf32_split(bvv[j][0], bh0, bl0);
+      tf32_split(bvv[j][1], bh1, bl1);
+      mma_tf32(c[j], al, bh0, bh1);
+      mma_tf32(c[j], ah, bl0, bl1);
+      mma_tf32(c[j], ah, bh0, bh1);
+    }
+    if (++since_flush == 4) {
+      since_flush = 0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ctot[j][q] += c[j][q]; c[j][q] = 0.f; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ctot[j][q] += c[j][q];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    sred[wid][(g) * 16 + 8 * j + 2 * t] = ctot[j][0];
+    sred[wid][(g) * 16 + 8 * j + 2 * t + 1] = ctot[j][1];
+    sred[wid][(g + 8) * 16 + 8 * j + 2 * t] = ctot[j][2];
+    sred[wid][(g + 8) * 16 + 8 * j + 2 * t + 1] = ctot[j][3];
+  }
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += sred[w][tid];
+  const int ci = tid >> 4, j = tid & 15;
+  if (ci < nci && j < nb) partials[((size_t)blockIdx.x * Cin + ci0 + ci) * CK + b0 + j] = sum;
 }
 
 // Per-channel sum of a view over (N, H*W): ConvTranspose2d bias gradient. partials [N*chunks][C].
@@ -879,7 +1004,7 @@ int ocrs_det_dw_bwd(const float* g, long long g_ss, const float* x, long long x_
 int ocrs_det_pool2_bwd(const float* x, long long x_ss, int N, int C, int H, int W, const float* sc,
                        const float* sh, const float* lo, const float* dout, long long dout_ss,
                        float* din, long long din_ss, void* stream) {
-  dim3 block(32, 8), grid(ocrs_cdiv(W, 32), ocrs_cdiv(H, 8), N * C);
+  dim3 block(32, 8), grid(ocrs_cdiv((W + 1) / 2, 32), ocrs_cdiv((H + 1) / 2, 8), N * C);
   pool2_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, dout, dout_ss,
                                                              din, din_ss);
   OCRS_CHECK_LAUNCH("pool2_bwd_kernel");
@@ -911,8 +1036,12 @@ int ocrs_det_convt_wgrad(const float* x, long long x_ss, int N, int Cin, int Hin
                          const float* isc, const float* ish, const float* ilo, const float* dout,
                          long long dout_ss, int Cout, int Hs, int Ws, float* partials, void* stream) {
   dim3 grid(ocrs_det_convt_wgrad_workers(N, Hin, Win), ocrs_cdiv(Cin, 16) * ocrs_cdiv(Cout * 9, 16));
-  convt_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout,
-                                                             dout_ss, Cout, Hs, Ws, N, partials);
+  if (getenv("OCRS_CONVT_WGRAD_SIMT"))
+    convt_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout, dout_ss,
+                                                               Cout, Hs, Ws, N, partials);
+  else
+    convt_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout,
+                                                                   dout_ss, Cout, Hs, Ws, N, partials);
   OCRS_CHECK_LAUNCH("convt_wgrad_kernel");
   return 0;
 }

@@ -169,27 +169,37 @@ __global__ void __launch_bounds__(256, 2) gemm_kernel(GemmArgs g) {
   }
 }
 
-// col[m][ (ky*kw + kx)*C + c ] = x[n][oy+ky-ph][ox+kx-pw][c]  (NHWC, zero padding)
-__global__ void im2col_nhwc_kernel(const float* __restrict__ x, int N, int H, int W, int C, int kh,
-                                   int kw, int ph, int pw, int Ho, int Wo, float* __restrict__ col) {
-  const int C4 = C >> 2;
-  const long long total = (long long)N * Ho * Wo * kh * kw * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long long r = i / C4;
-    const int tap = (int)(r % (kh * kw));
-    r /= kh * kw;
-    const int ox = (int)(r % Wo);
-    r /= Wo;
-    const int oy = (int)(r % Ho);
-    const int n = (int)(r / Ho);
+// col[m][ (ky*kw + kx)*C + c ] = x[n][oy+ky-ph][ox+kx-pw][c]  (NHWC, zero padding).
+// grid.x = output pixel (n, oy, ox) groups, one warp-row of threads per (tap, 4 channels): no per-element
+// 64-bit index arithmetic, 16-byte loads and stores, writes of a block are one contiguous span of col.
+constexpr int I2C_PIX = 4;  // output pixels per block
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const float* __restrict__ x, int N, int H, int W, int C, int kh, int kw, int ph,
+                   int pw, int Ho, int Wo, float* __restrict__ col) {
+  const int C4 = C >> 2, row4 = kh * kw * C4;  // float4 per col row
+  const long long npix = (long long)N * Ho * Wo;
+  const long long p0 = (long long)blockIdx.x * I2C_PIX;
+  __shared__ int spix[I2C_PIX][3];
+  if (threadIdx.x < I2C_PIX) {
+    const long long p = p0 + threadIdx.x;
+    const long long q = p / Wo;
+    spix[threadIdx.x][0] = (int)(q / Ho);
+    spix[threadIdx.x][1] = (int)(q % Ho);
+    spix[threadIdx.x][2] = (int)(p % Wo);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < I2C_PIX * row4; e += 256) {
+    const int pl = e / row4, r = e - pl * row4;
+    const long long p = p0 + pl;
+    if (p >= npix) break;
+    const int tap = r / C4, c4 = r - tap * C4;
+    const int n = spix[pl][0], oy = spix[pl][1], ox = spix[pl][2];
     const int ky = tap / kw, kx = tap - ky * kw;
     const int iy = oy + ky - ph, ix = ox + kx - pw;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W)
       v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * C + c4 * 4);
-    reinterpret_cast<float4*>(col)[i] = v;
+    reinterpret_cast<float4*>(col)[(size_t)p * row4 + r] = v;
   }
 }
 
@@ -250,9 +260,10 @@ int ocrs_gemm_splits(int K, int splits) {
 int ocrs_im2col_nhwc(const float* x, int N, int H, int W, int C, int kh, int kw, int ph, int pw, int Ho,
                      int Wo, float* col, void* stream) {
   OCRS_CHECK_ARG(C % 4 == 0, "im2col: channel count %d must be a multiple of 4", C);
-  const long long total = (long long)N * Ho * Wo * kh * kw * (C / 4);
-  const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  im2col_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, ph, pw, Ho, Wo, col);
+  const long long npix = (long long)N * Ho * Wo;
+  const long long blocks = (npix + I2C_PIX - 1) / I2C_PIX;
+  OCRS_CHECK_ARG(blocks < 2147483647LL, "im2col: too many pixels");
+  im2col_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, ph, pw, Ho, Wo, col);
   OCRS_CHECK_LAUNCH("im2col_nhwc_kernel");
   return 0;
 }
