@@ -191,13 +191,24 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
     // this frame's gradient row from alpha(t) + beta(t)
     for (int c = lane; c < C; c += 32) occ[c] = 0.f;
     __syncwarp();
+    // Half of the lattice states are blanks: their posterior mass is reduced across the warp with
+    // shuffles instead of contending on one shared-memory word; labels use (rarely colliding) atomics.
+    float blank_mass = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (lane * K + k < L) {
+      const int s = lane * K + k;
+      if (s < L) {
         const float v = av[k] + b[k] + nl - cur[k];
-        if (v > -INFINITY) atomicAdd(&occ[lab[k]], expf(v));
+        if (v > -INFINITY) {
+          const float e = expf(v);
+          if (s & 1) atomicAdd(&occ[lab[k]], e);
+          else blank_mass += e;
+        }
       }
     }
+    blank_mass = warp_sum(blank_mass);
+    __syncwarp();
+    if (lane == 0) occ[blank] += blank_mass;
     __syncwarp();
     float* g = grad + (size_t)t * tstride + (size_t)n * C;
     for (int c = lane; c < C; c += 32) g[c] = (expf(row[c]) - occ[c]) * gs;
