@@ -13,19 +13,36 @@
 namespace {
 
 constexpr int CTC_WARPS = 4;
+constexpr int CTC_DEPTH_F = 8;  // frames of log-probs in flight per warp (forward)
+constexpr int CTC_DEPTH_B = 6;  // frames of (log-probs, alpha) in flight per warp (backward)
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// The lattice runs in the log2 domain (log-probs are scaled by log2(e) on load) so that every
+// log-sum-exp is MUFU.EX2 x3 + MUFU.LG2 with no range reduction, and unreachable states carry the
+// finite sentinel NEG instead of -inf so the recurrence needs no branches: the serial chain of a
+// step is ~15 dependent instructions per state. ex2/lg2.approx are accurate to ~2^-22, far below
+// the fp32 drift of a 200-step lattice.
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, NEG = -1e30f;
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-  float m = fmaxf(a, fmaxf(b, c));
-  if (m == -INFINITY) return -INFINITY;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  const float m = fmaxf(a, fmaxf(b, c));
+  return m + lg2(ex2(a - m) + ex2(b - m) + ex2(c - m));
 }
 
 template <int K>
-__global__ void __launch_bounds__(CTC_WARPS * 32)
+__global__ void __launch_bounds__(CTC_WARPS * 32, K <= 3 ? 12 : (K <= 6 ? 8 : 4))
 ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, int tgt_stride,
                  const int* __restrict__ in_len, const int* __restrict__ tgt_len,
                  float* __restrict__ alpha, float* __restrict__ nll, int T, int N, int C,
                  int blank) {
+  extern __shared__ float ring_all[];
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * CTC_WARPS + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -34,10 +51,12 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, 
   const int L = 2 * S + 1;
   const int Tn = min(in_len[n], T);
   const int* tg = targets + (size_t)n * tgt_stride;
-
+  if (Tn <= 0) {
+    if (lane == 0) nll[n] = (S == 0) ? 0.f : INFINITY;
+    return;
+  }
   int lab[K];
   bool skip[K];
-  float a[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int s = lane * K + k;
@@ -50,50 +69,58 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, 
     lab[k] = l;
     skip[k] = sk;
   }
-  float* arow = alpha + (size_t)n * T * LROW + lane * K;
-  if (Tn <= 0) {
-    if (lane == 0) nll[n] = (S == 0) ? 0.f : INFINITY;
-    return;
-  }
-  const float* row = lp + (size_t)n * C;
   const size_t tstride = (size_t)N * C;
-  float cur[K], nxt[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) cur[k] = (lane * K + k < L) ? row[lab[k]] : 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int s = lane * K + k;
-    a[k] = (s < 2 && s < L) ? cur[k] : -INFINITY;
-    arow[k] = a[k];
-  }
-  for (int t = 1; t < Tn; ++t) {
-    row += tstride;
-#pragma unroll
-    for (int k = 0; k < K; ++k) nxt[k] = (lane * K + k < L) ? row[lab[k]] : 0.f;
-    // neighbours owned by the previous lane
-    float p1 = __shfl_up_sync(0xffffffffu, a[K - 1], 1);
-    float p2 = __shfl_up_sync(0xffffffffu, K >= 2 ? a[K >= 2 ? K - 2 : 0] : -INFINITY, 1);
-    if (K == 1) {
-      // with one state per lane s-2 lives two lanes back
-      p2 = __shfl_up_sync(0xffffffffu, a[0], 2);
-      if (lane < 2) p2 = -INFINITY;
+  // log-prob rows stream through a per-warp shared-memory ring, CTC_DEPTH_F frames ahead (cp.async)
+  float* ring = ring_all + (size_t)(threadIdx.x >> 5) * CTC_DEPTH_F * C;
+  const float* isrc = lp + (size_t)n * C + lane;  // frame to stage next (this lane's first column)
+  auto issue = [&](int t) {
+    if (t < Tn) {
+      float* dst = ring + (t % CTC_DEPTH_F) * C + lane;
+      for (int c = 0; c + lane < C; c += 32) cp_async4(dst + c, isrc + c);
     }
-    if (lane == 0) { p1 = -INFINITY; p2 = -INFINITY; }
-    float an[K];
+    isrc += tstride;
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int d = 0; d < CTC_DEPTH_F; ++d) issue(d);
+  float a[K];
+  float* arow = alpha + (size_t)n * T * LROW + lane * K;
+  for (int t = 0; t < Tn; ++t) {
+    cp_async_wait<CTC_DEPTH_F - 1>();
+    __syncwarp();
+    const float* slot = ring + (t % CTC_DEPTH_F) * C;
+    float e[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float m1 = (k >= 1) ? a[k >= 1 ? k - 1 : 0] : p1;
-      const float m2 = (k >= 2) ? a[k >= 2 ? k - 2 : 0] : ((k == 1) ? p1 : p2);
-      // (k == 1) uses previous lane's last state as s-2, (k == 0) its second-to-last
-      const float s2 = skip[k] ? m2 : -INFINITY;
-      an[k] = (lane * K + k < L) ? lse3(a[k], m1, s2) + nxt[k] : -INFINITY;
+    for (int k = 0; k < K; ++k) e[k] = slot[lab[k]] * LOG2E;
+    __syncwarp();
+    issue(t + CTC_DEPTH_F);
+    if (t == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int s = lane * K + k;
+        a[k] = (s < 2 && s < L) ? e[k] : NEG;
+      }
+    } else {
+      float p1 = __shfl_up_sync(0xffffffffu, a[K - 1], 1);
+      float p2 = __shfl_up_sync(0xffffffffu, a[K >= 2 ? K - 2 : 0], K >= 2 ? 1 : 2);
+      if (lane == 0) { p1 = NEG; p2 = NEG; }
+      if (K == 1 && lane < 2) p2 = NEG;
+      float an[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float m1 = (k >= 1) ? a[k >= 1 ? k - 1 : 0] : p1;
+        const float m2 = (k >= 2) ? a[k >= 2 ? k - 2 : 0] : ((k == 1 && K >= 2) ? p1 : p2);
+        an[k] = (lane * K + k < L) ? lse3(a[k], m1, skip[k] ? m2 : NEG) + e[k] : NEG;
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[k] = fmaxf(an[k], NEG);
     }
+#pragma unroll
+    for (int k = 0; k < K; ++k) arow[k] = a[k];
     arow += LROW;
-#pragma unroll
-    for (int k = 0; k < K; ++k) { a[k] = an[k]; arow[k] = an[k]; }
   }
   // nll = -logsumexp(alpha[Tn-1][L-1], alpha[Tn-1][L-2])
-  float last = -INFINITY, last2 = -INFINITY;
+  float last = NEG, last2 = NEG;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int s = lane * K + k;
@@ -103,15 +130,14 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, 
   last = warp_max(last);
   last2 = warp_max(last2);
   if (lane == 0) {
-    float m = fmaxf(last, last2);
-    float r = (m == -INFINITY) ? -INFINITY : m + logf(expf(last - m) + expf(last2 - m));
-    nll[n] = -r;
+    const float r = lse3(last, last2, NEG);
+    nll[n] = (r < -1e29f) ? INFINITY : -r * LN2;
   }
 }
 
 // mode: 0 = none (gout[n]), 1 = mean (gout[0] / (N * max(S,1))), 2 = sum (gout[0])
 template <int K>
-__global__ void __launch_bounds__(CTC_WARPS * 32)
+__global__ void __launch_bounds__(CTC_WARPS * 32, K <= 3 ? 8 : (K <= 6 ? 5 : 3))
 ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targets,
                      int tgt_stride, const int* __restrict__ in_len,
                      const int* __restrict__ tgt_len, const float* __restrict__ alpha,
@@ -135,6 +161,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
   if (mode == 1) gs /= ((float)N * (float)max(S, 1));
   const float nl = nll[n];
   const bool dead = zero_infinity && (nl == INFINITY);
+  const float nl2 = nl * LOG2E;
 
   // frames at or beyond the sample's input length get zero gradient
   for (int t = max(Tn, 0); t < T; ++t) {
@@ -165,28 +192,57 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
     skip[k] = sk;
   }
 
-  float b[K];
-  const float* arow = alpha + ((size_t)n * T + (Tn - 1)) * LROW + lane * K;
-  const float* row = lp + (size_t)(Tn - 1) * tstride + (size_t)n * C;
-  float cur[K], av[K];
+  // Per-warp ring of CTC_DEPTH_B frames, each [C log-probs | 32*K alphas], filled by cp.async.
+  const int slot_floats = C + LROW;
+  float* ring = occ_all + CTC_WARPS * C + (size_t)wid * CTC_DEPTH_B * slot_floats;
+  const float* isrc = lp + (size_t)(Tn - 1) * tstride + (size_t)n * C + lane;
+  const float* asrc = alpha + ((size_t)n * T + (Tn - 1)) * LROW + lane * K;
+  auto issue = [&](int t) {
+    if (t >= 0) {
+      float* dst = ring + (t % CTC_DEPTH_B) * slot_floats;
+      for (int c = 0; c + lane < C; c += 32) cp_async4(dst + lane + c, isrc + c);
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int s = lane * K + k;
-    cur[k] = (s < L) ? row[lab[k]] : 0.f;
-    av[k] = arow[k];
-    b[k] = (s < L && s >= L - 2) ? cur[k] : -INFINITY;
-  }
+      for (int k = 0; k < K; ++k) cp_async4(dst + C + lane * K + k, asrc + k);
+    }
+    isrc -= tstride;
+    asrc -= LROW;
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int d = 0; d < CTC_DEPTH_B; ++d) issue(Tn - 1 - d);
+  float b[K];
+  float* gptr = grad + (size_t)(Tn - 1) * tstride + (size_t)n * C;
   for (int t = Tn - 1; t >= 0; --t) {
-    // prefetch t-1
-    float nxt[K], an[K];
-    const float* prow = row - tstride;
-    const float* parow = arow - LROW;
-    if (t > 0) {
+    cp_async_wait<CTC_DEPTH_B - 1>();
+    __syncwarp();
+    const float* slot = ring + (t % CTC_DEPTH_B) * slot_floats;
+    float cur[K], av[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      cur[k] = slot[lab[k]] * LOG2E;
+      av[k] = slot[C + lane * K + k];
+    }
+    // beta(t)[s] = lse(beta(t+1)[s], beta(t+1)[s+1], skip ? beta(t+1)[s+2]) + lp[t][l_s]
+    if (t == Tn - 1) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        nxt[k] = (lane * K + k < L) ? prow[lab[k]] : 0.f;
-        an[k] = parow[k];
+        const int s = lane * K + k;
+        b[k] = (s < L && s >= L - 2) ? cur[k] : NEG;
       }
+    } else {
+      float n1 = __shfl_down_sync(0xffffffffu, b[0], 1);
+      float n2 = __shfl_down_sync(0xffffffffu, b[K >= 2 ? 1 : 0], K >= 2 ? 1 : 2);
+      if (lane == 31) { n1 = NEG; n2 = NEG; }
+      if (K == 1 && lane >= 30) n2 = NEG;
+      float bn[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float u1 = (k + 1 < K) ? b[k + 1 < K ? k + 1 : 0] : n1;
+        const float u2 = (k + 2 < K) ? b[k + 2 < K ? k + 2 : 0] : ((k + 1 < K) ? n1 : n2);
+        bn[k] = (lane * K + k < L) ? lse3(b[k], u1, skip[k] ? u2 : NEG) + cur[k] : NEG;
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) b[k] = fmaxf(bn[k], NEG);
     }
     // this frame's gradient row from alpha(t) + beta(t)
     for (int c = lane; c < C; c += 32) occ[c] = 0.f;
@@ -198,9 +254,9 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
     for (int k = 0; k < K; ++k) {
       const int s = lane * K + k;
       if (s < L) {
-        const float v = av[k] + b[k] + nl - cur[k];
-        if (v > -INFINITY) {
-          const float e = expf(v);
+        const float v = av[k] + b[k] + nl2 - cur[k];
+        if (v > -1e29f) {
+          const float e = ex2(v);
           if (s & 1) atomicAdd(&occ[lab[k]], e);
           else blank_mass += e;
         }
@@ -208,34 +264,11 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
     }
     blank_mass = warp_sum(blank_mass);
     __syncwarp();
-    if (lane == 0) occ[blank] += blank_mass;
+    for (int c = lane; c < C; c += 32)
+      gptr[c] = (ex2(slot[c] * LOG2E) - occ[c] - (c == blank ? blank_mass : 0.f)) * gs;
+    gptr -= tstride;
     __syncwarp();
-    float* g = grad + (size_t)t * tstride + (size_t)n * C;
-    for (int c = lane; c < C; c += 32) g[c] = (expf(row[c]) - occ[c]) * gs;
-    __syncwarp();
-    if (t == 0) break;
-    // beta(t-1)[s] = lse(beta(t)[s], beta(t)[s+1], skip ? beta(t)[s+2]) + lp[t-1][l_s]
-    float n1 = __shfl_down_sync(0xffffffffu, b[0], 1);
-    float n2 = __shfl_down_sync(0xffffffffu, K >= 2 ? b[K >= 2 ? 1 : 0] : -INFINITY, 1);
-    if (K == 1) {
-      n2 = __shfl_down_sync(0xffffffffu, b[0], 2);
-      if (lane >= 30) n2 = -INFINITY;
-    }
-    if (lane == 31) { n1 = -INFINITY; n2 = -INFINITY; }
-    float bn[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float u1 = (k + 1 < K) ? b[k + 1 < K ? k + 1 : 0] : n1;
-      const float u2 = (k + 2 < K) ? b[k + 2 < K ? k + 2 : 0] : ((k + 1 < K) ? n1 : n2);
-      // (k == K-2) takes next lane's first state as s+2, (k == K-1) its second
-      const float s2 = skip[k] ? u2 : -INFINITY;
-      const int s = lane * K + k;
-      bn[k] = (s < L) ? lse3(b[k], (s + 1 < L) ? u1 : -INFINITY, s2) + nxt[k] : -INFINITY;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) { b[k] = bn[k]; cur[k] = nxt[k]; av[k] = an[k]; }
-    row = prow;
-    arow = parow;
+    issue(t - CTC_DEPTH_B);  // frame t is consumed: refill its slot
   }
 }
 
@@ -293,7 +326,11 @@ int ocrs_ctc_fwd(const float* log_probs, const int* targets, int tgt_stride,
   OCRS_CHECK_ARG(K_ > 0, "ctc_fwd: target length %d exceeds supported maximum 255", max_S);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ocrs_cdiv(N, CTC_WARPS);
-  CTC_DISPATCH(K_, (ctc_alpha_kernel<K><<<grid, CTC_WARPS * 32, 0, st>>>(
+  const size_t fsmem = (size_t)CTC_WARPS * CTC_DEPTH_F * C * sizeof(float);
+  OCRS_CHECK_ARG(fsmem <= 200 * 1024, "ctc_fwd: class count %d too large", C);
+  if (fsmem > 48 * 1024)
+    CTC_DISPATCH(K_, (cudaFuncSetAttribute(ctc_alpha_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)));
+  CTC_DISPATCH(K_, (ctc_alpha_kernel<K><<<grid, CTC_WARPS * 32, fsmem, st>>>(
                        log_probs, targets, tgt_stride, input_lengths, target_lengths, alpha, nll,
                        T, N, C, blank)));
   OCRS_CHECK_LAUNCH("ctc_alpha_kernel");
@@ -313,8 +350,10 @@ int ocrs_ctc_bwd(const float* log_probs, const int* targets, int tgt_stride,
   OCRS_CHECK_ARG(K_ > 0, "ctc_bwd: target length %d exceeds supported maximum 255", max_S);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ocrs_cdiv(N, CTC_WARPS);
-  const size_t smem = (size_t)CTC_WARPS * C * sizeof(float);
-  OCRS_CHECK_ARG(smem <= 48 * 1024, "ctc_bwd: class count %d too large", C);
+  const size_t smem = (size_t)CTC_WARPS * (C + (size_t)CTC_DEPTH_B * (C + 32 * K_)) * sizeof(float);
+  OCRS_CHECK_ARG(smem <= 200 * 1024, "ctc_bwd: class count %d / target length too large for the staging ring", C);
+  if (smem > 48 * 1024)
+    CTC_DISPATCH(K_, (cudaFuncSetAttribute(ctc_beta_grad_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   CTC_DISPATCH(K_, (ctc_beta_grad_kernel<K><<<grid, CTC_WARPS * 32, smem, st>>>(
                        log_probs, targets, tgt_stride, input_lengths, target_lengths, alpha, nll,
                        grad_out, reduction, zero_infinity, grad_log_probs, T, N, C, blank)));
