@@ -40,6 +40,14 @@ struct TcArgs {
   int a_mn, b_mn;        // operand is MN-major (stored [K][rows])
   int bn;                // tile columns (UMMA N)
   uint32_t idesc;
+  // Implicit-GEMM 3x3 / pad-1 convolution (forward and dgrad): A is the NHWC activation viewed as
+  // [M = N*H*W rows][cC channels]; the k-block (tap, channel chunk) is the SAME 2-D TMA box shifted by
+  // (ky-1)*W + (kx-1) rows (im2col folded into the TMA coordinates, never materialised), and the rows
+  // whose tap falls outside the image are zeroed by the converter warps while they split hi/lo.
+  // conv == 2: weight gradient dW[co][(tap, ci)] = sum_pixels dY[p][co] * x[p + shift(tap)][ci]: A = dY
+  // (MN-major, plain), B = the activation (MN-major) where every 32-channel chunk of the N tile belongs
+  // to one tap and is loaded with that tap's row shift; out-of-image pixels are zeroed by the converter.
+  int conv, cH, cW, cC;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,12 +156,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
-        mbar_expect_tx(full_bar(s), A_TILE_BYTES + b_bytes);
+        uint32_t tx_bytes = A_TILE_BYTES + b_bytes;
+        if (g.conv == 2) {
+          int nvalid = 0;
+          for (int c = 0; c < g.bn / 32; ++c) nvalid += (n0 + 32 * c < 9 * g.cC) ? 1 : 0;
+          tx_bytes = A_TILE_BYTES + (uint32_t)nvalid * 4096u;
+        }
+        mbar_expect_tx(full_bar(s), tx_bytes);
         const int k0 = (kb0 + i) * TBK;
-        if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0, full_bar(s));
+        if (g.conv == 1) {
+          const int cpb = g.cC / TBK, kb = kb0 + i;
+          const int tap = kb / cpb, c0 = (kb - tap * cpb) * TBK;
+          tma_load_2d(sa, &map_a, c0, m0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
+        } else if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0, full_bar(s));
         else
           for (int c = 0; c < TBM / 32; ++c) tma_load_2d(sa + c * 4096, &map_a, m0 + 32 * c, k0, full_bar(s));
-        if (!g.b_mn) tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
+        if (g.conv == 2) {
+          for (int c = 0; c < g.bn / 32; ++c) {
+            const int col = n0 + 32 * c;
+            if (col < 9 * g.cC) {
+              const int tap = col / g.cC, ci0 = col - tap * g.cC;
+              tma_load_2d(sb + c * 4096, &map_b, ci0, k0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
+            }
+          }
+        } else if (!g.b_mn) tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
         else
           for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0, full_bar(s));
       }
@@ -192,6 +218,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ---- converter: split landed fp32 tiles into TF32-exact hi (in place) and lo ----
     const int ct = threadIdx.x - 64;  // 0..127
     const int a_vec = A_TILE_BYTES / 16, b_vec = (int)b_bytes / 16;
+    // conv mode: this thread always converts tile rows (ct >> 3) + 16 i; 9-bit tap validity per row
+    uint32_t rmask[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rmask[i] = 0x1ffu;
+    // wgrad mode: this thread converts B k-rows (ct >> 3) and (ct >> 3) + 16 of each 32-channel chunk
+    int wtap[4] = {0, 0, 0, 0};
+    bool wchunk[4] = {false, false, false, false};
+    int woy[2] = {0, 0}, wox[2] = {0, 0};
+    if (g.conv == 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = n0 + 32 * c;
+        wchunk[c] = c < g.bn / 32 && col < 9 * g.cC;
+        wtap[c] = wchunk[c] ? col / g.cC : 0;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long m = (long long)kb0 * TBK + (ct >> 3) + 16 * e;
+        wox[e] = (int)(m % g.cW);
+        woy[e] = (int)((m / g.cW) % g.cH);
+      }
+    }
+    if (g.conv == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (ct >> 3) + 16 * i;
+        const int ox = m % g.cW, oy = (m / g.cW) % g.cH;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+          if (iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW) bits |= 1u << tap;
+        }
+        rmask[i] = bits;
+      }
+    }
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -209,8 +271,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         hi[idx] = h;
         lo[idx] = l;
       };
-      for (int j = ct; j < a_vec; j += 128) split(ah, al, j);
-      for (int j = ct; j < b_vec; j += 128) split(bh, bl, j);
+      if (g.conv == 1) {
+        const int tap = (kb0 + i) / (g.cC / TBK);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = ct + 128 * q;
+          if ((rmask[q] >> tap) & 1u) split(ah, al, j);
+          else { ah[j] = make_float4(0.f, 0.f, 0.f, 0.f); al[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+      } else {
+        for (int j = ct; j < a_vec; j += 128) split(ah, al, j);
+      }
+      if (g.conv == 2) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = q >> 1, e = q & 1, j = ct + 128 * q;
+          if (j < b_vec) {
+            const int iy = woy[e] + wtap[c] / 3 - 1, ix = wox[e] + wtap[c] % 3 - 1;
+            if (wchunk[c] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW) split(bh, bl, j);
+            else { bh[j] = make_float4(0.f, 0.f, 0.f, 0.f); bl[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {  // advance this thread's two pixels by one k-block (32 pixels)
+          wox[e] += TBK;
+          while (wox[e] >= g.cW) { wox[e] -= g.cW; if (++woy[e] == g.cH) woy[e] = 0; }
+        }
+      } else {
+        for (int j = ct; j < b_vec; j += 128) split(bh, bl, j);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(conv_bar(s));
     }
@@ -346,7 +435,7 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
   else          { if (make_map(&ma, A, M, K, lda, 32, TBK, true)) return -1; }
   if (b_kmajor) { if (make_map(&mb, B, K, N, ldb, TBK, bn, false)) return -1; }
   else          { if (make_map(&mb, B, N, K, ldb, 32, TBK, true)) return -1; }
-  TcArgs g{C, ldc, M, N, K, bias, relu, accumulate, stats, 0, !a_kmajor, !b_kmajor, bn, 0};
+  TcArgs g{C, ldc, M, N, K, bias, relu, accumulate, stats, 0, !a_kmajor, !b_kmajor, bn, 0, 0, 0, 0, 0};
   const int total_kb = ocrs_cdiv(K, TBK);
   g.kb_per_split = ocrs_cdiv(total_kb, splits);
   const int zs = ocrs_cdiv(total_kb, g.kb_per_split);
@@ -356,6 +445,64 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
   dim3 grid(ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs);
   gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
   OCRS_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+
+// 3x3 / pad-1 / stride-1 convolution as an implicit GEMM on the tensor cores (no im2col buffer):
+// x: NHWC [N][H][W][Cin] (Cin % 32 == 0), wp: [Cout][(ky, kx, ci)], out: [N*H*W][ldc].
+// Forward convolution and, with the flipped/transposed weights, the data gradient.
+int ocrs_conv3x3_tc(const float* x, int N, int H, int W, int Cin, const float* wp, int Cout, float* out,
+                    long long ldc, const float* bias, int relu, float* stats, void* stream) {
+  OCRS_CHECK_ARG(Cin % TBK == 0 && Cin > 0, "conv3x3_tc: Cin %d must be a multiple of 32", Cin);
+  OCRS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)wp % 16 == 0), "conv3x3_tc: operands must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long Ml = (long long)N * H * W;
+  OCRS_CHECK_ARG(Ml < 2147483647LL - 128, "conv3x3_tc: too many pixels");
+  const int M = (int)Ml, K = 9 * Cin;
+  const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+  CUtensorMap ma, mb;
+  if (make_map(&ma, x, Cin, M, Cin, TBK, TBM, false)) return -1;
+  if (make_map(&mb, wp, K, Cout, K, TBK, bn, false)) return -1;
+  TcArgs g{out, ldc, M, Cout, K, bias, relu, 0, stats, K / TBK, 0, 0, bn, 0, 1, H, W, Cin};
+  g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  dim3 grid(ocrs_cdiv(Cout, bn), ocrs_cdiv(M, TBM), 1);
+  gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
+  OCRS_CHECK_LAUNCH("gemm_tc_kernel(conv3x3)");
+  return 0;
+}
+
+// Weight gradient of the same convolution, also without an im2col buffer:
+// dwp[z][Cout][(ky, kx, ci)] (split-K partials, z < ocrs_gemm_tc_splits(N*H*W, splits)) from
+// dy: [N*H*W][Cout] and x: NHWC [N][H][W][Cin]. Cin % 32 == 0, Cout % 4 == 0.
+int ocrs_conv3x3_wgrad_tc(const float* dy, const float* x, int N, int H, int W, int Cin, int Cout,
+                          float* dwp, int splits, void* stream) {
+  OCRS_CHECK_ARG(Cin % TBK == 0 && Cout % 4 == 0, "conv3x3_wgrad_tc: unsupported channel counts %d -> %d", Cin, Cout);
+  OCRS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0), "conv3x3_wgrad_tc: operands must be 16-byte aligned");
+  OCRS_CHECK_ARG(splits >= 1, "conv3x3_wgrad_tc: bad split count");
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long Kl = (long long)N * H * W;
+  OCRS_CHECK_ARG(Kl < 2147483647LL - 128, "conv3x3_wgrad_tc: too many pixels");
+  const int K = (int)Kl, Nn = 9 * Cin, bn = 128;
+  CUtensorMap ma, mb;
+  if (make_map(&ma, dy, Cout, K, Cout, 32, TBK, true)) return -1;
+  if (make_map(&mb, x, Cin, K, Cin, 32, TBK, true)) return -1;
+  TcArgs g{dwp, Nn, Cout, Nn, K, nullptr, 0, 0, nullptr, 0, 1, 1, bn, 0, 2, H, W, Cin};
+  const int total_kb = ocrs_cdiv(K, TBK);
+  g.kb_per_split = ocrs_cdiv(total_kb, splits);
+  const int zs = ocrs_cdiv(total_kb, g.kb_per_split);
+  g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
+            ((uint32_t)(TBM >> 4) << 24);
+  dim3 grid(ocrs_cdiv(Nn, bn), ocrs_cdiv(Cout, TBM), zs);
+  gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
+  OCRS_CHECK_LAUNCH("gemm_tc_kernel(conv3x3 wgrad)");
   return 0;
 }
 

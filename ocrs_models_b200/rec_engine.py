@@ -26,6 +26,39 @@ GEMM_BACKEND = os.environ.get("OCRS_GEMM", "tc")
 GRU_BACKEND = os.environ.get("OCRS_GRU", "persist")
 # OCRS_EXACT_FWD=1 runs the forward convolutions on the fp32-FMA GEMM instead of the tensor cores.
 EXACT_FWD = os.environ.get("OCRS_EXACT_FWD", "0") == "1"
+# Implicit-GEMM 3x3 convolutions (im2col folded into the TMA coordinates); OCRS_IMPLICIT=0 goes back to
+# an explicit im2col buffer + GEMM.
+IMPLICIT = os.environ.get("OCRS_IMPLICIT", "1") == "1"
+
+
+def conv3x3(x, N, H, W, cin, wp, cout, st, bias=None, relu=False, stats=None):
+    """3x3 / pad 1 convolution of an NHWC tensor on the tensor cores without an im2col buffer.
+    wp: [cout, (ky, kx, ci)]. Returns [N*H*W, cout]."""
+    out = _empty((N * H * W, cout), x.device)
+    call("ocrs_conv3x3_tc", ptr(x), N, H, W, cin, ptr(wp), cout, ptr(out), cout, ptr(bias), int(relu), ptr(stats), st,
+         meta=2.0 * N * H * W * cout * 9 * cin)
+    return out
+
+
+def conv3x3_wgrad(dy, x, N, H, W, cin, cout, st):
+    """[cout, (ky, kx, ci)] weight gradient of conv3x3 from dy [N*H*W, cout] and the NHWC input x."""
+    lib = _lib.lib()
+    K = N * H * W
+    tiles = ((9 * cin + 127) // 128) * ((cout + 127) // 128)
+    want = max(1, min(TARGET_BLOCKS // tiles, K // 256))
+    splits = lib.ocrs_gemm_tc_splits(K, want)
+    part = _empty((splits, cout, 9 * cin), x.device)
+    call("ocrs_conv3x3_wgrad_tc", ptr(dy), ptr(x), N, H, W, cin, cout, ptr(part), splits, st,
+         meta=2.0 * K * cout * 9 * cin)
+    if splits == 1:
+        return part[0]
+    out = _empty((cout, 9 * cin), x.device)
+    call("ocrs_finalize_partials", ptr(part), splits, cout * 9 * cin, ptr(out), st)
+    return out
+
+
+def _implicit_ok(cin, kh):
+    return IMPLICIT and GEMM_BACKEND == "tc" and not EXACT_FWD and kh == 3 and cin % 32 == 0
 
 
 def _empty(shape, dev):
@@ -152,13 +185,20 @@ class _RecFunction(torch.autograd.Function):
             call("ocrs_rec_conv0_fwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(a0), st)
 
             def conv_bn_pool(inp, Hh, Ww, cin, conv, bn, ph, pw, mode, relu, kh=3, pad=1, out_strides=None, out=None):
-                col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, kh, kh, pad, pad, st)
-                M = N * Ho * Wo
                 cout = conv.out_channels
-                rows = lib.ocrs_gemm_stat_rows(M)
-                stats = _empty((rows, 2, cout), dev) if training else None
-                y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1], st,
-                         stats=stats, exact=EXACT_FWD)
+                if _implicit_ok(cin, kh):
+                    col, Ho, Wo = None, Hh, Ww
+                    M = N * Ho * Wo
+                    rows = lib.ocrs_gemm_stat_rows(M)
+                    stats = _empty((rows, 2, cout), dev) if training else None
+                    y = conv3x3(inp, N, Hh, Ww, cin, _w_fwd(conv.weight), cout, st, stats=stats)
+                else:
+                    col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, kh, kh, pad, pad, st)
+                    M = N * Ho * Wo
+                    rows = lib.ocrs_gemm_stat_rows(M)
+                    stats = _empty((rows, 2, cout), dev) if training else None
+                    y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1],
+                             st, stats=stats, exact=EXACT_FWD)
                 bs = _bn_finalize(bn, stats, rows, M, training, relu, st, dev)
                 Hp, Wp = Ho // ph, Wo // pw
                 if out is None:
@@ -166,15 +206,18 @@ class _RecFunction(torch.autograd.Function):
                     out_strides = (Hp * Wp * cout, Wp * cout, cout)
                 call("ocrs_rec_bn_act_pool_fwd", ptr(y), N, Ho, Wo, cout, ph, pw, mode, int(relu), ptr(bs.scale),
                      ptr(bs.shift), ptr(out), *out_strides, st)
-                return out, Hp, Wp, dict(col=col, y=y, bs=bs, geom=(Ho, Wo, cout, ph, pw, mode, int(relu)),
+                return out, Hp, Wp, dict(col=col, inp=inp, y=y, bs=bs, geom=(Ho, Wo, cout, ph, pw, mode, int(relu)),
                                          ostr=out_strides, inp_geom=(Hh, Ww, cin), k=(kh, pad))
 
             def conv_bias_relu(inp, Hh, Ww, cin, conv):
+                if _implicit_ok(cin, 3):
+                    a = conv3x3(inp, N, Hh, Ww, cin, _w_fwd(conv.weight), conv.out_channels, st, bias=conv.bias, relu=True)
+                    return a, dict(col=None, inp=inp, a=a, inp_geom=(Hh, Ww, cin))
                 col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, 3, 3, 1, 1, st)
                 M = N * Ho * Wo
                 a = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, conv.out_channels,
                          col.shape[1], st, bias=conv.bias, relu=True, exact=EXACT_FWD)
-                return a, dict(col=col, a=a, inp_geom=(Hh, Ww, cin))
+                return a, dict(col=col, inp=inp, a=a, inp_geom=(Hh, Ww, cin))
 
             a3, H3, W3, rec["3"] = conv_bn_pool(a0, H1, W1, 32, cv["3"], cv["4"], 2, 2, 0, True)
             a7, rec["7"] = conv_bias_relu(a3, H3, W3, 64, cv["7"])
@@ -300,17 +343,23 @@ class _RecFunction(torch.autograd.Function):
 
             def conv_bwd(r, conv, dy, Ho, Wo, need_dx=True):
                 """dy: [N, Ho, Wo, Cout] gradient of the raw conv output. Returns d(input) NHWC."""
+                Hh, Ww, cin = r["inp_geom"]
+                kh, pad = r.get("k", (3, 1))
                 col = r["col"]
-                M, K = col.shape
                 cout = conv.out_channels
-                dwp = gemm(dy, cout, False, col, K, False, cout, K, M, st, split_ok=True)
+                if col is None:  # implicit GEMM: the weight gradient gathers the activation by TMA as well
+                    M = N * Hh * Ww
+                    dwp = conv3x3_wgrad(dy, r["inp"], N, Hh, Ww, cin, cout, st)
+                else:
+                    M, K = col.shape
+                    dwp = gemm(dy, cout, False, col, K, False, cout, K, M, st, split_ok=True)
                 grads[id(conv.weight)] = _w_grad_back(dwp, conv.weight)
                 if conv.bias is not None:
                     grads[id(conv.bias)] = colsum(dy, cout, M, cout, st, dev)
                 if not need_dx:
                     return None
-                Hh, Ww, cin = r["inp_geom"]
-                kh, pad = r.get("k", (3, 1))
+                if _implicit_ok(cout, kh):
+                    return conv3x3(dy, N, Ho, Wo, cout, _w_dgrad(conv.weight), cin, st)
                 dcol, Hi, Wi = im2col(dy, N, Ho, Wo, cout, kh, kh, kh - 1 - pad, kh - 1 - pad, st)
                 assert (Hi, Wi) == (Hh, Ww)
                 return gemm(dcol, dcol.shape[1], True, _w_dgrad(conv.weight), dcol.shape[1], True, N * Hh * Ww, cin,

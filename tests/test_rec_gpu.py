@@ -62,6 +62,40 @@ def test_gemm_column_stats(backend, monkeypatch):
     assert rel_l2(out, A.double() @ B.double().t()) < 1e-5
 
 
+@pytest.mark.parametrize("N,H,W,cin,cout", [(2, 16, 200, 128, 128), (3, 7, 13, 32, 64), (1, 32, 40, 64, 128), (2, 5, 9, 128, 32), (1, 1, 1, 32, 64)])
+def test_implicit_gemm_conv3x3(N, H, W, cin, cout):
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200.rec_engine import _w_dgrad, _w_fwd, conv3x3
+
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    rows = _lib.lib().ocrs_gemm_stat_rows(N * H * W)
+    stats = torch.empty(rows, 2, cout, device="cuda")
+    out = conv3x3(xd, N, H, W, cin, _w_fwd(w.cuda()), cout, _st(), bias=b.cuda(), stats=stats)
+    assert rel_l2(out.reshape(N, H, W, cout).permute(0, 3, 1, 2), ref) < 3e-6
+    assert rel_l2(stats[:, 0].sum(0), out.sum(0)) < 1e-5
+    out = conv3x3(xd, N, H, W, cin, _w_fwd(w.cuda()), cout, _st(), bias=b.cuda(), relu=True)
+    assert rel_l2(out.reshape(N, H, W, cout).permute(0, 3, 1, 2), torch.relu(ref)) < 3e-6
+    # data gradient = the same kernel on dY with flipped / transposed weights
+    dy = torch.randn(N, cout, H, W, generator=g)
+    dref = F.conv_transpose2d(dy.double(), w.double(), padding=1)
+    dyd = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    dx = conv3x3(dyd, N, H, W, cout, _w_dgrad(w.cuda()), cin, _st())
+    assert rel_l2(dx.reshape(N, H, W, cin).permute(0, 3, 1, 2), dref) < 3e-6
+    # weight gradient, also gathered by TMA (no im2col buffer)
+    from ocrs_models_b200.rec_engine import _w_grad_back, conv3x3_wgrad
+
+    xg = x.double().requires_grad_(True)
+    wg = w.double().requires_grad_(True)
+    F.conv2d(xg, wg, None, padding=1).backward(dy.double())
+    dwp = conv3x3_wgrad(dyd.reshape(N * H * W, cout), xd, N, H, W, cin, cout, _st())
+    assert rel_l2(_w_grad_back(dwp, w), wg.grad) < 5e-6
+
+
 def test_conv0_fwd_bwd():
     from ocrs_models_b200._lib import call, lib, ptr
 
