@@ -9,10 +9,10 @@
 // to the fourth; the epilogue adds them in round-to-nearest fp32. Error ~5e-7 at K = 1152, on par
 // with an fp32 FMA loop.
 //
-// One CTA per 128 x BN output tile (BN in {32, 64, 128}), 192 threads:
+// One CTA per 128 x BN output tile (BN in {32, 64, 128}), 320 threads:
 //   warp 0      TMA producer: fp32 operand tiles -> 128B-swizzled shared memory (3 stages)
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, accumulator in TMEM)
-//   warps 2-5   split each landed stage into hi / lo tiles in place, then the epilogue:
+//   warps 2-9   split each landed stage into hi / lo tiles in place; warps 2-5 then run the epilogue:
 //               tcgen05.ld TMEM -> registers -> (+bias, ReLU) -> smem tile -> coalesced global
 //               stores (+ per-column sum / sum^2 partials for a following BatchNorm)
 // Operands may be K-major (X[rows][K]) or MN-major (X[K][rows]); the latter is what the weight
@@ -108,7 +108,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -132,7 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 128);
+      mbar_init(conv_bar(s), 256);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -216,34 +216,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ---- converter: split landed fp32 tiles into TF32-exact hi (in place) and lo ----
-    const int ct = threadIdx.x - 64;  // 0..127
-    const int a_vec = A_TILE_BYTES / 16, b_vec = (int)b_bytes / 16;
-    // conv mode: this thread always converts tile rows (ct >> 3) + 16 i; 9-bit tap validity per row
-    uint32_t rmask[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) rmask[i] = 0x1ffu;
-    // wgrad mode: this thread converts B k-rows (ct >> 3) and (ct >> 3) + 16 of each 32-channel chunk
-    int wtap[4] = {0, 0, 0, 0};
-    bool wchunk[4] = {false, false, false, false};
-    int woy[2] = {0, 0}, wox[2] = {0, 0};
-    if (g.conv == 2) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = n0 + 32 * c;
-        wchunk[c] = c < g.bn / 32 && col < 9 * g.cC;
-        wtap[c] = wchunk[c] ? col / g.cC : 0;
-      }
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const long long m = (long long)kb0 * TBK + (ct >> 3) + 16 * e;
-        wox[e] = (int)(m % g.cW);
-        woy[e] = (int)((m / g.cW) % g.cH);
-      }
-    }
+    // 8 warps (2 per scheduler). Each thread owns 4 float4 of A and 4 of B per stage; all eight are
+    // loaded before any is stored so the shared-memory latency overlaps.
+    const int ct = threadIdx.x - 64;  // 0..255
+    const int b_vec = (int)b_bytes / 16;
+    // conv == 1: this thread converts A tile rows (ct >> 3) + 32 q; 9-bit tap validity per row
+    uint32_t rmask[4] = {0x1ffu, 0x1ffu, 0x1ffu, 0x1ffu};
     if (g.conv == 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (ct >> 3) + 16 * i;
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + (ct >> 3) + 32 * q;
         const int ox = m % g.cW, oy = (m / g.cW) % g.cH;
         uint32_t bits = 0;
 #pragma unroll
@@ -251,58 +233,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
           if (iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW) bits |= 1u << tap;
         }
-        rmask[i] = bits;
+        rmask[q] = bits;
       }
     }
+    // conv == 2: this thread converts B k-row (ct >> 3) of each of the four 32-channel chunks
+    int wtap[4] = {0, 0, 0, 0};
+    bool wchunk[4] = {false, false, false, false};
+    int woy = 0, wox = 0;
+    if (g.conv == 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = n0 + 32 * c;
+        wchunk[c] = c < g.bn / 32 && col < 9 * g.cC;
+        wtap[c] = wchunk[c] ? col / g.cC : 0;
+      }
+      const long long m = (long long)kb0 * TBK + (ct >> 3);
+      wox = (int)(m % g.cW);
+      woy = (int)((m / g.cW) % g.cH);
+    }
+    auto split4 = [](const float4& v, float4& h, float4& l) {
+      h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
+      h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
+      h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
+      h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
+    };
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
       float4* ah = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
-      float4* al = ah + a_vec;
-      float4* bh = al + a_vec;
-      float4* bl = bh + a_vec;
-      auto split = [](float4* hi, float4* lo, int idx) {
-        float4 v = hi[idx], h, l;
-        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
-        hi[idx] = h;
-        lo[idx] = l;
-      };
-      if (g.conv == 1) {
-        const int tap = (kb0 + i) / (g.cC / TBK);
+      float4* al = ah + A_TILE_BYTES / 16;
+      float4* bh = al + A_TILE_BYTES / 16;
+      float4* bl = bh + A_TILE_BYTES / 16;
+      float4 va[4], vb[4];
+      bool ka[4], kb_[4];  // keep (true) or zero (false)
+      const int tap_a = g.conv == 1 ? (kb0 + i) / (g.cC / TBK) : 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int j = ct + 128 * q;
-          if ((rmask[q] >> tap) & 1u) split(ah, al, j);
-          else { ah[j] = make_float4(0.f, 0.f, 0.f, 0.f); al[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      for (int q = 0; q < 4; ++q) {
+        const int j = ct + 256 * q;
+        ka[q] = (rmask[q] >> tap_a) & 1u;
+        kb_[q] = j < b_vec;
+        if (g.conv == 2) {
+          const int iy = woy + wtap[q] / 3 - 1, ix = wox + wtap[q] % 3 - 1;
+          kb_[q] = kb_[q] && wchunk[q] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW;
         }
-      } else {
-        for (int j = ct; j < a_vec; j += 128) split(ah, al, j);
+        va[q] = ah[j];
+        vb[q] = (j < b_vec) ? bh[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (g.conv == 2) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c = q >> 1, e = q & 1, j = ct + 128 * q;
-          if (j < b_vec) {
-            const int iy = woy[e] + wtap[c] / 3 - 1, ix = wox[e] + wtap[c] % 3 - 1;
-            if (wchunk[c] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW) split(bh, bl, j);
-            else { bh[j] = make_float4(0.f, 0.f, 0.f, 0.f); bl[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
-          }
+      for (int q = 0; q < 4; ++q) {
+        const int j = ct + 256 * q;
+        float4 h, l;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        split4(ka[q] ? va[q] : z, h, l);
+        ah[j] = h;
+        al[j] = l;
+        if (j < b_vec) {
+          split4(kb_[q] ? vb[q] : z, h, l);
+          bh[j] = h;
+          bl[j] = l;
         }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {  // advance this thread's two pixels by one k-block (32 pixels)
-          wox[e] += TBK;
-          while (wox[e] >= g.cW) { wox[e] -= g.cW; if (++woy[e] == g.cH) woy[e] = 0; }
-        }
-      } else {
-        for (int j = ct; j < b_vec; j += 128) split(bh, bl, j);
+      }
+      if (g.conv == 2) {  // advance this thread's pixel by one k-block (32 pixels)
+        wox += TBK;
+        while (wox >= g.cW) { wox -= g.cW; if (++woy == g.cH) woy = 0; }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(conv_bar(s));
     }
+    if (warp >= 6) goto teardown;  // only the first four converter warps own a TMEM lane quarter
     // ---- epilogue ----
     mbar_wait(tmem_full_bar, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -365,6 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   }
+teardown:
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -443,7 +443,7 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
             ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
   dim3 grid(ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs);
-  gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
+  gemm_tc_kernel<<<grid, 320, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
   OCRS_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }
@@ -470,7 +470,7 @@ int ocrs_conv3x3_tc(const float* x, int N, int H, int W, int Cin, const float* w
   TcArgs g{out, ldc, M, Cout, K, bias, relu, 0, stats, K / TBK, 0, 0, bn, 0, 1, H, W, Cin};
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
   dim3 grid(ocrs_cdiv(Cout, bn), ocrs_cdiv(M, TBM), 1);
-  gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
+  gemm_tc_kernel<<<grid, 320, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
   OCRS_CHECK_LAUNCH("gemm_tc_kernel(conv3x3)");
   return 0;
 }
@@ -501,7 +501,7 @@ int ocrs_conv3x3_wgrad_tc(const float* dy, const float* x, int N, int H, int W, 
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
             ((uint32_t)(TBM >> 4) << 24);
   dim3 grid(ocrs_cdiv(Nn, bn), ocrs_cdiv(Cout, TBM), zs);
-  gemm_tc_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
+  gemm_tc_kernel<<<grid, 320, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
   OCRS_CHECK_LAUNCH("gemm_tc_kernel(conv3x3 wgrad)");
   return 0;
 }
