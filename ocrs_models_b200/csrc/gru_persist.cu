@@ -4,10 +4,12 @@
 //
 // The recurrence is latency-bound: each step is a [N,256] x [256,768] product that depends on the
 // previous one. Work decomposition: one CLUSTER OF 4 CTAs per (direction, group of 4 batch rows).
-// Each CTA keeps its quarter of W_hh (64 hidden units x 3 gates x 256, fp32, 204 KB) resident in
-// shared memory for the whole sequence; per step it computes its 64 units for the 4 rows, applies
+// Each CTA (512 threads = 16 warps, so shared-memory latency overlaps) keeps its quarter of W_hh (64
+// hidden units x 3 gates x 256, fp32, 204 KB) resident in shared memory for the whole sequence; per step it computes its 64 units for the 4 rows, applies
 // the gate non-linearities, and broadcasts the 256 new h values to the other three CTAs through
-// distributed shared memory; one cluster barrier per step. h never round-trips through HBM/L2;
+// distributed shared memory; one cluster barrier per step, split into
+// arrive / wait around the global stores. (A register-resident-weights variant with clusters of 8 was
+// measured slower: the DSMEM broadcast volume doubles.) h never round-trips through HBM/L2;
 // only the per-step outputs are written (fire and forget) and gi (the precomputed input
 // projection) is prefetched one step ahead. Batch groups are independent, so N = 64 is
 // 2 x 16 clusters = 128 CTAs, one wave on 148 SMs.
@@ -32,6 +34,22 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// Sum v[0..3] over the 4 lanes {kq & 3}; lane kq returns the total of v[kq & 3] (2 + 1 shuffles).
+__device__ __forceinline__ float reduce4_transpose(const float (&v)[4], int kq) {
+  float b[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = (kq & 2) ? v[j] : v[j + 2];
+    const float keep = (kq & 2) ? v[j + 2] : v[j];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float send = (kq & 1) ? b[0] : b[1];
+  const float keep = (kq & 1) ? b[1] : b[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 struct FwdArgs {
   const float* gi[2];    // [T*N][768]
   const float* whh[2];   // [768][256]
@@ -41,7 +59,7 @@ struct FwdArgs {
   int T, N, groups;      // groups = ceil(N / RB)
 };
 
-__global__ void __launch_bounds__(256, 1) gru_fwd_persist_kernel(FwdArgs p) {
+__global__ void __launch_bounds__(512, 1) gru_fwd_persist_kernel(FwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;                      // [3*UQ][LDW]
   float* hs = smem + 3 * UQ * LDW;       // [2][RB][H]
@@ -50,22 +68,22 @@ __global__ void __launch_bounds__(256, 1) gru_fwd_persist_kernel(FwdArgs p) {
   const int cid = blockIdx.x / 4;        // cluster id
   const int d = cid / p.groups, grp = cid % p.groups;
   const int n0 = grp * RB, u0 = rank * UQ;
-  const int tid = threadIdx.x, jl = tid >> 2, kq = tid & 3;
+  const int tid = threadIdx.x, jl = tid >> 3, kq = tid & 7;
   const int T = p.T, N = p.N;
 
   // resident weight slice: smem row g*UQ + j  <-  W_hh row g*256 + u0 + j
   const float* w = p.whh[d];
-  for (int i = tid; i < 3 * UQ * (H / 4); i += 256) {
+  for (int i = tid; i < 3 * UQ * (H / 4); i += 512) {
     const int row = i / (H / 4), c4 = i % (H / 4);
     const int g = row / UQ, j = row % UQ;
     const float4 v = *reinterpret_cast<const float4*>(w + (size_t)(g * H + u0 + j) * H + c4 * 4);
     *reinterpret_cast<float4*>(Ws + row * LDW + c4 * 4) = v;
   }
-  for (int i = tid; i < 2 * RB * H; i += 256) hs[i] = 0.f;
+  for (int i = tid; i < 2 * RB * H; i += 512) hs[i] = 0.f;
   const int u = u0 + jl;
   const float br = p.bhh[d][u], bz = p.bhh[d][H + u], bn = p.bhh[d][2 * H + u];
-  const int n = n0 + kq;                 // the batch row this lane finalises
-  const bool live = n < N;
+  const int n = n0 + (kq & 3);           // the batch row this lane finalises (lanes kq >= 4 mirror kq - 4)
+  const bool live = n < N && kq < 4;
   float* remote[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) remote[r] = cluster.map_shared_rank(hs, r);
@@ -95,9 +113,9 @@ __global__ void __launch_bounds__(256, 1) gru_fwd_persist_kernel(FwdArgs p) {
 #pragma unroll
     for (int b = 0; b < RB; ++b) { acc[b][0] = 0.f; acc[b][1] = 0.f; acc[b][2] = 0.f; }
     const float4* h4 = reinterpret_cast<const float4*>(hs + buf * RB * H);
-#pragma unroll 4
-    for (int i = 0; i < H / 16; ++i) {
-      const int k4 = i * 4 + kq;
+#pragma unroll
+    for (int i = 0; i < H / 32; ++i) {
+      const int k4 = i * 8 + kq;
       const float4 wr = W4[(0 * UQ + jl) * (LDW / 4) + k4];
       const float4 wz = W4[(1 * UQ + jl) * (LDW / 4) + k4];
       const float4 wn = W4[(2 * UQ + jl) * (LDW / 4) + k4];
@@ -109,32 +127,35 @@ __global__ void __launch_bounds__(256, 1) gru_fwd_persist_kernel(FwdArgs p) {
         acc[b][2] = dot4(hv, wn, acc[b][2]);
       }
     }
-    float ar = 0.f, az = 0.f, an = 0.f;
+    float tot[3];
 #pragma unroll
-    for (int b = 0; b < RB; ++b)
+    for (int g = 0; g < 3; ++g) {
+      float v[RB];
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        float v = acc[b][g];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (b == kq) { if (g == 0) ar = v; else if (g == 1) az = v; else an = v; }
-      }
-    const float hp = hs[buf * RB * H + kq * H + u];
+      for (int b = 0; b < RB; ++b) v[b] = acc[b][g] + __shfl_xor_sync(0xffffffffu, acc[b][g], 4);
+      tot[g] = reduce4_transpose(v, kq);
+    }
+    const float ar = tot[0], az = tot[1], an = tot[2];
+    const int row = kq & 3;
+    const float hp = hs[buf * RB * H + row * H + u];
     const float r = sigm(gr + ar + br);
     const float z = sigm(gz + az + bz);
     const float ghn = an + bn;
     const float nn = tanhf(gn + r * ghn);
     const float hnew = (1.f - z) * nn + z * hp;
-    const int off = (buf ^ 1) * RB * H + kq * H + u;
+    const int off = (buf ^ 1) * RB * H + row * H + u;
+    if (kq < 4) {
 #pragma unroll
-    for (int rk = 0; rk < 4; ++rk) remote[rk][off] = hnew;
+      for (int rk = 0; rk < 4; ++rk) remote[rk][off] = hnew;
+    }
+    cluster_arrive();
     if (live) {
       p.out[((size_t)t * N + n) * 512 + d * H + u] = hnew;
       float* gs = p.gates + (((size_t)t * N + n) * 2 + d) * 4 * H;
       gs[u] = r; gs[H + u] = z; gs[2 * H + u] = nn; gs[3 * H + u] = ghn;
     }
     gr = ngr; gz = ngz; gn = ngn;
-    cluster.sync();
+    cluster_wait();
   }
 }
 
@@ -148,7 +169,7 @@ struct BwdArgs {
   int T, N, groups;
 };
 
-__global__ void __launch_bounds__(256, 1) gru_bwd_persist_kernel(BwdArgs p) {
+__global__ void __launch_bounds__(512, 1) gru_bwd_persist_kernel(BwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   float* Wt = smem;                  // [UQ][LDT]
   float* dg = smem + UQ * LDT;       // [2][RB][G3]
@@ -157,19 +178,19 @@ __global__ void __launch_bounds__(256, 1) gru_bwd_persist_kernel(BwdArgs p) {
   const int cid = blockIdx.x / 4;
   const int d = cid / p.groups, grp = cid % p.groups;
   const int n0 = grp * RB, u0 = rank * UQ;
-  const int tid = threadIdx.x, kl = tid >> 2, jq = tid & 3;
+  const int tid = threadIdx.x, kl = tid >> 3, jq = tid & 7;
   const int T = p.T, N = p.N;
 
   const float* wt = p.whhT[d];
-  for (int i = tid; i < UQ * (G3 / 4); i += 256) {
+  for (int i = tid; i < UQ * (G3 / 4); i += 512) {
     const int row = i / (G3 / 4), c4 = i % (G3 / 4);
     const float4 v = *reinterpret_cast<const float4*>(wt + (size_t)(u0 + row) * G3 + c4 * 4);
     *reinterpret_cast<float4*>(Wt + row * LDT + c4 * 4) = v;
   }
-  for (int i = tid; i < 2 * RB * G3; i += 256) dg[i] = 0.f;
+  for (int i = tid; i < 2 * RB * G3; i += 512) dg[i] = 0.f;
   const int u = u0 + kl;
-  const int n = n0 + jq;
-  const bool live = n < N;
+  const int n = n0 + (jq & 3);
+  const bool live = n < N && jq < 4;
   float* remote[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) remote[r] = cluster.map_shared_rank(dg, r);
@@ -193,40 +214,40 @@ __global__ void __launch_bounds__(256, 1) gru_bwd_persist_kernel(BwdArgs p) {
 #pragma unroll
     for (int b = 0; b < RB; ++b) acc[b] = 0.f;
     const float4* g4 = reinterpret_cast<const float4*>(dg + buf * RB * G3);
-#pragma unroll 4
-    for (int i = 0; i < G3 / 16; ++i) {
-      const int j4 = i * 4 + jq;
+#pragma unroll 8
+    for (int i = 0; i < G3 / 32; ++i) {
+      const int j4 = i * 8 + jq;
       const float4 wv = W4[kl * (LDT / 4) + j4];
 #pragma unroll
       for (int b = 0; b < RB; ++b) acc[b] = dot4(g4[b * (G3 / 4) + j4], wv, acc[b]);
     }
-    float a = 0.f;
+    float v4[RB];
 #pragma unroll
-    for (int b = 0; b < RB; ++b) {
-      float v = acc[b];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (b == jq) a = v;
-    }
+    for (int b = 0; b < RB; ++b) v4[b] = acc[b] + __shfl_xor_sync(0xffffffffu, acc[b], 4);
+    const float a = reduce4_transpose(v4, jq);
+    const int row = jq & 3;
     const float dh = go + a + carry;
     const float dn = dh * (1.f - z) * (1.f - nn * nn);
     const float dz = dh * (hp - nn) * z * (1.f - z);
     const float dr = dn * ghn * r * (1.f - r);
     carry = dh * z;
-    const int off = (buf ^ 1) * RB * G3 + jq * G3;
+    const int off = (buf ^ 1) * RB * G3 + row * G3;
+    if (jq < 4) {
 #pragma unroll
-    for (int rk = 0; rk < 4; ++rk) {
-      remote[rk][off + u] = dr;
-      remote[rk][off + H + u] = dz;
-      remote[rk][off + 2 * H + u] = dn * r;
+      for (int rk = 0; rk < 4; ++rk) {
+        remote[rk][off + u] = dr;
+        remote[rk][off + H + u] = dz;
+        remote[rk][off + 2 * H + u] = dn * r;
+      }
     }
+    cluster_arrive();
     if (live) {
       float* gi = p.dgi[d] + ((size_t)t * N + n) * G3;
       float* gh = p.dgh[d] + ((size_t)t * N + n) * G3;
       gi[u] = dr; gi[H + u] = dz; gi[2 * H + u] = dn;
       gh[u] = dr; gh[H + u] = dz; gh[2 * H + u] = dn * r;
     }
-    cluster.sync();
+    cluster_wait();
   }
 }
 
@@ -234,7 +255,7 @@ template <typename Args>
 int launch_cluster(void (*kern)(Args), Args a, int clusters, int smem, cudaStream_t st, const char* name) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * 4);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(512);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
