@@ -28,7 +28,7 @@ constexpr int TBK = 32;           // fp32 elements per k-block = one 128-byte sw
 constexpr int STAGES = 3;
 constexpr int A_TILE_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 4 * A_TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo (B sized for BN = 128)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 4096 /*BN partials*/;
 
 struct TcArgs {
   float* C; long long ldc;
@@ -48,6 +48,8 @@ struct TcArgs {
   // (MN-major, plain), B = the activation (MN-major) where every 32-channel chunk of the N tile belongs
   // to one tap and is loaded with that tap's row shift; out-of-image pixels are zeroed by the converter.
   int conv, cH, cW, cC;
+  int tiles_m, tiles_n, zs;  // tile grid walked by the persistent CTAs
+  int nbuf;                  // TMEM accumulator sets (2 when 4*bn <= 256 columns)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,26 +110,48 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-__global__ void __launch_bounds__(320, 1)
+// Sum over the 32 lanes of v[j], for every j at once: lane j returns column j's total (31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float send = up ? v[j] : v[j + o];
+      const float keep = up ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+constexpr int NUM_THREADS = 448;   // warp 0 TMA, warp 1 MMA, warps 2-9 converters, warps 10-13 epilogue
+constexpr int EPI_THREAD0 = 320;
+
+// Persistent kernel: CTA b walks tiles b, b + gridDim.x, ... (n fastest, then m, then split-K slice).
+// The stage ring and its mbarrier phases run continuously across tiles, so the TMA producer and the
+// converter warps prefetch the next tile while the epilogue warps drain the finished accumulators; with
+// 4*bn <= 256 TMEM columns the accumulators are double-buffered and the drain is hidden completely.
+template <int CONV>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar0 = base + STAGES * STAGE_BYTES;
-  // barriers: full[s] = bar0 + 8 s ; conv[s] = +24 ; empty[s] = +48 ; tmem_full = +72 ; tmem ptr at +80
+  // barriers: full[s] = bar0 + 8 s ; conv[s] = +24 ; empty[s] = +48 ; tmem_full[b] = +72 ; tmem_empty[b] = +88
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto conv_bar = [&](int s) { return bar0 + 24u + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 48u + 8u * s; };
-  const uint32_t tmem_full_bar = bar0 + 72u;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 80);
+  auto tmem_full_bar = [&](int b) { return bar0 + 72u + 8u * b; };
+  auto tmem_empty_bar = [&](int b) { return bar0 + 88u + 8u * b; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 112);
+  float* sm_stats = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + 128);  // [4 chunks][4 warps][2][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * g.bn;
   const int total_kb = (g.K + TBK - 1) / TBK;
-  const int kb0 = blockIdx.z * g.kb_per_split;
-  const int kb1 = min(total_kb, kb0 + g.kb_per_split);
-  const int nkb = kb1 - kb0;
   const uint32_t b_bytes = (uint32_t)g.bn * TBK * 4;
+  const int total_tiles = g.tiles_m * g.tiles_n * g.zs;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -135,7 +159,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(conv_bar(s), 256);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -149,222 +176,297 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+#define TILE_DECODE(tile_)                                         \
+  const int tn_ = (tile_) % g.tiles_n, tr_ = (tile_) / g.tiles_n;  \
+  const int tm_ = tr_ % g.tiles_m, tz_ = tr_ / g.tiles_m;          \
+  const int m0 = tm_ * TBM, n0 = tn_ * g.bn;                       \
+  const int kb0 = tz_ * g.kb_per_split;                            \
+  const int nkb = min(total_kb, kb0 + g.kb_per_split) - kb0;       \
+  (void)m0; (void)n0; (void)kb0; (void)tz_; (void)tm_;
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TILE_DECODE(tile)
         uint32_t tx_bytes = A_TILE_BYTES + b_bytes;
-        if (g.conv == 2) {
+        if (CONV == 2) {
           int nvalid = 0;
           for (int c = 0; c < g.bn / 32; ++c) nvalid += (n0 + 32 * c < 9 * g.cC) ? 1 : 0;
           tx_bytes = A_TILE_BYTES + (uint32_t)nvalid * 4096u;
         }
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        const int k0 = (kb0 + i) * TBK;
-        if (g.conv == 1) {
-          const int cpb = g.cC / TBK, kb = kb0 + i;
-          const int tap = kb / cpb, c0 = (kb - tap * cpb) * TBK;
-          tma_load_2d(sa, &map_a, c0, m0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
-        } else if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0, full_bar(s));
-        else
-          for (int c = 0; c < TBM / 32; ++c) tma_load_2d(sa + c * 4096, &map_a, m0 + 32 * c, k0, full_bar(s));
-        if (g.conv == 2) {
-          for (int c = 0; c < g.bn / 32; ++c) {
-            const int col = n0 + 32 * c;
-            if (col < 9 * g.cC) {
-              const int tap = col / g.cC, ci0 = col - tap * g.cC;
-              tma_load_2d(sb + c * 4096, &map_b, ci0, k0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          const int k0 = (kb0 + i) * TBK;
+          if (CONV == 1) {
+            const int cpb = g.cC / TBK, kb = kb0 + i;
+            const int tap = kb / cpb, c0 = (kb - tap * cpb) * TBK;
+            tma_load_2d(sa, &map_a, c0, m0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
+          } else if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0, full_bar(s));
+          else
+            for (int c = 0; c < TBM / 32; ++c) tma_load_2d(sa + c * 4096, &map_a, m0 + 32 * c, k0, full_bar(s));
+          if (CONV == 2) {
+            for (int c = 0; c < g.bn / 32; ++c) {
+              const int col = n0 + 32 * c;
+              if (col < 9 * g.cC) {
+                const int tap = col / g.cC, ci0 = col - tap * g.cC;
+                tma_load_2d(sb + c * 4096, &map_b, ci0, k0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
+              }
             }
-          }
-        } else if (!g.b_mn) tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
-        else
-          for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0, full_bar(s));
+          } else if (!g.b_mn) tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
+          else
+            for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0, full_bar(s));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(conv_bar(s), ph);
+      // K-major (SWIZZLE_128B): 8 rows x 128 B atoms 1024 B apart (SBO), k-step = +32 B inside the row.
+      // MN-major (SWIZZLE_128B_BASE32B): 32-wide MN chunks 4096 B apart (LBO), atoms of 4 k-rows
+      // 512 B apart (SBO), k-step (8 k-rows) = +1024 B.
+      const uint32_t a_lbo = g.a_mn ? 4096u : 16u, b_lbo = g.b_mn ? 4096u : 16u;
+      const uint32_t a_sbo = g.a_mn ? 512u : 1024u, b_sbo = g.b_mn ? 512u : 1024u;
+      const uint32_t a_lt = g.a_mn ? 1u : 2u, b_lt = g.b_mn ? 1u : 2u;
+      const uint32_t a_step = g.a_mn ? 1024u : 32u, b_step = g.b_mn ? 1024u : 32u;
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        TILE_DECODE(tile)
+        const uint32_t buf = lt % (uint32_t)g.nbuf, use = lt / (uint32_t)g.nbuf;
+        mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
-        // K-major (SWIZZLE_128B): 8 rows x 128 B atoms 1024 B apart (SBO), k-step = +32 B inside the row.
-        // MN-major (SWIZZLE_128B_BASE32B): 32-wide MN chunks 4096 B apart (LBO), atoms of 4 k-rows
-        // 512 B apart (SBO), k-step (8 k-rows) = +1024 B.
-        const uint32_t a_lbo = g.a_mn ? 4096u : 16u, b_lbo = g.b_mn ? 4096u : 16u;
-        const uint32_t a_sbo = g.a_mn ? 512u : 1024u, b_sbo = g.b_mn ? 512u : 1024u;
-        const uint32_t a_lt = g.a_mn ? 1u : 2u, b_lt = g.b_mn ? 1u : 2u;
-        const uint32_t a_step = g.a_mn ? 1024u : 32u, b_step = g.b_mn ? 1024u : 32u;
+        const uint32_t tb = tmem_base + buf * 256u;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(conv_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_TILE_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < TBK / 8; ++ks) {
-          const uint64_t ah = make_desc(sa + ks * a_step, a_lbo, a_sbo, a_lt);
-          const uint64_t al = make_desc(sa + A_TILE_BYTES + ks * a_step, a_lbo, a_sbo, a_lt);
-          const uint64_t bh = make_desc(sb + ks * b_step, b_lbo, b_sbo, b_lt);
-          const uint64_t bl = make_desc(sb + A_TILE_BYTES + ks * b_step, b_lbo, b_sbo, b_lt);
-          // accumulator columns: [0,bn) [bn,2bn) [2bn,3bn) = hi.hi round-robin, [3bn,4bn) = cross terms
-          umma_tf32(tmem_base + (uint32_t)((i % 3) * g.bn), ah, bh, g.idesc, (i >= 3 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_base + (uint32_t)(3 * g.bn), ah, bl, g.idesc, (i > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_base + (uint32_t)(3 * g.bn), al, bh, g.idesc, 1u);
+          for (int ks = 0; ks < TBK / 8; ++ks) {
+            const uint64_t ah = make_desc(sa + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t al = make_desc(sa + A_TILE_BYTES + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t bh = make_desc(sb + ks * b_step, b_lbo, b_sbo, b_lt);
+            const uint64_t bl = make_desc(sb + A_TILE_BYTES + ks * b_step, b_lbo, b_sbo, b_lt);
+            // accumulator columns: [0,bn) [bn,2bn) [2bn,3bn) = hi.hi round-robin, [3bn,4bn) = cross terms
+            umma_tf32(tb + (uint32_t)((i % 3) * g.bn), ah, bh, g.idesc, (i >= 3 || ks > 0) ? 1u : 0u);
+            umma_tf32(tb + (uint32_t)(3 * g.bn), ah, bl, g.idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32(tb + (uint32_t)(3 * g.bn), al, bh, g.idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        umma_commit(tmem_full_bar(buf));
       }
-      umma_commit(tmem_full_bar);
     }
-  } else {
-    // ---- converter: split landed fp32 tiles into TF32-exact hi (in place) and lo ----
+  } else if (threadIdx.x < EPI_THREAD0) {
+    // ---- converters: split landed fp32 tiles into TF32-exact hi (in place) and lo ----
     // 8 warps (2 per scheduler). Each thread owns 4 float4 of A and 4 of B per stage; all eight are
     // loaded before any is stored so the shared-memory latency overlaps.
     const int ct = threadIdx.x - 64;  // 0..255
     const int b_vec = (int)b_bytes / 16;
-    // conv == 1: this thread converts A tile rows (ct >> 3) + 32 q; 9-bit tap validity per row
-    uint32_t rmask[4] = {0x1ffu, 0x1ffu, 0x1ffu, 0x1ffu};
-    if (g.conv == 1) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int m = m0 + (ct >> 3) + 32 * q;
-        const int ox = m % g.cW, oy = (m / g.cW) % g.cH;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
-          if (iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW) bits |= 1u << tap;
-        }
-        rmask[q] = bits;
-      }
-    }
-    // conv == 2: this thread converts B k-row (ct >> 3) of each of the four 32-channel chunks
-    int wtap[4] = {0, 0, 0, 0};
-    bool wchunk[4] = {false, false, false, false};
-    int woy = 0, wox = 0;
-    if (g.conv == 2) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = n0 + 32 * c;
-        wchunk[c] = c < g.bn / 32 && col < 9 * g.cC;
-        wtap[c] = wchunk[c] ? col / g.cC : 0;
-      }
-      const long long m = (long long)kb0 * TBK + (ct >> 3);
-      wox = (int)(m % g.cW);
-      woy = (int)((m / g.cW) % g.cH);
-    }
     auto split4 = [](const float4& v, float4& h, float4& l) {
       h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
       h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
       h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
       h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
     };
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-      mbar_wait(full_bar(s), ph);
-      float4* ah = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
-      float4* al = ah + A_TILE_BYTES / 16;
-      float4* bh = al + A_TILE_BYTES / 16;
-      float4* bl = bh + A_TILE_BYTES / 16;
-      float4 va[4], vb[4];
-      bool ka[4], kb_[4];  // keep (true) or zero (false)
-      const int tap_a = g.conv == 1 ? (kb0 + i) / (g.cC / TBK) : 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TILE_DECODE(tile)
+      // CONV == 1: this thread converts A tile rows (ct >> 3) + 32 q; 9-bit tap validity per row
+      uint32_t rmask[4] = {0x1ffu, 0x1ffu, 0x1ffu, 0x1ffu};
+      if (CONV == 1) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = ct + 256 * q;
-        ka[q] = (rmask[q] >> tap_a) & 1u;
-        kb_[q] = j < b_vec;
-        if (g.conv == 2) {
-          const int iy = woy + wtap[q] / 3 - 1, ix = wox + wtap[q] % 3 - 1;
-          kb_[q] = kb_[q] && wchunk[q] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW;
-        }
-        va[q] = ah[j];
-        vb[q] = (j < b_vec) ? bh[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int q = 0; q < 4; ++q) {
+          const int m = m0 + (ct >> 3) + 32 * q;
+          const int ox = m % g.cW, oy = (m / g.cW) % g.cH;
+          uint32_t bits = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = ct + 256 * q;
-        float4 h, l;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        split4(ka[q] ? va[q] : z, h, l);
-        ah[j] = h;
-        al[j] = l;
-        if (j < b_vec) {
-          split4(kb_[q] ? vb[q] : z, h, l);
-          bh[j] = h;
-          bl[j] = l;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+            if (iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW) bits |= 1u << tap;
+          }
+          rmask[q] = bits;
         }
       }
-      if (g.conv == 2) {  // advance this thread's pixel by one k-block (32 pixels)
-        wox += TBK;
-        while (wox >= g.cW) { wox -= g.cW; if (++woy == g.cH) woy = 0; }
+      // CONV == 2: this thread converts B k-row (ct >> 3) of each of the four 32-channel chunks
+      int wdy[4] = {0, 0, 0, 0}, wdx[4] = {0, 0, 0, 0};
+      bool wchunk[4] = {false, false, false, false};
+      int woy = 0, wox = 0;
+      if (CONV == 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = n0 + 32 * c;
+          wchunk[c] = c < g.bn / 32 && col < 9 * g.cC;
+          const int tap = wchunk[c] ? col / g.cC : 0;
+          wdy[c] = tap / 3 - 1;
+          wdx[c] = tap % 3 - 1;
+        }
+        const long long m = (long long)kb0 * TBK + (ct >> 3);
+        wox = (int)(m % g.cW);
+        woy = (int)((m / g.cW) % g.cH);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(conv_bar(s));
+      int tap_a = 0, chunk_a = 0;  // CONV == 1: (tap, channel chunk) of the current k-block
+      const int cpb = CONV == 1 ? g.cC / TBK : 1;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        float4* ah = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
+        float4* al = ah + A_TILE_BYTES / 16;
+        float4* bh = al + A_TILE_BYTES / 16;
+        float4* bl = bh + A_TILE_BYTES / 16;
+        float4 va[4], vb[4];
+        bool ka[4], kb_[4];  // keep (true) or zero (false)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = ct + 256 * q;
+          ka[q] = CONV == 1 ? ((rmask[q] >> tap_a) & 1u) != 0 : true;
+          kb_[q] = j < b_vec;
+          if (CONV == 2) {
+            const int iy = woy + wdy[q], ix = wox + wdx[q];
+            kb_[q] = kb_[q] && wchunk[q] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW;
+          }
+          va[q] = ah[j];
+          vb[q] = (j < b_vec) ? bh[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = ct + 256 * q;
+          float4 h, l;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          split4(ka[q] ? va[q] : z, h, l);
+          ah[j] = h;
+          al[j] = l;
+          if (j < b_vec) {
+            split4(kb_[q] ? vb[q] : z, h, l);
+            bh[j] = h;
+            bl[j] = l;
+          }
+        }
+        if (CONV == 1) {
+          if (++chunk_a == cpb) { chunk_a = 0; ++tap_a; }
+        }
+        if (CONV == 2) {  // advance this thread's pixel by one k-block (32 pixels)
+          wox += TBK;
+          while (wox >= g.cW) { wox -= g.cW; if (++woy == g.cH) woy = 0; }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(conv_bar(s));
+      }
     }
-    if (warp >= 6) goto teardown;  // only the first four converter warps own a TMEM lane quarter
-    // ---- epilogue ----
-    mbar_wait(tmem_full_bar, 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;                // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;         // tile row held by this thread
-    float* ct_s = reinterpret_cast<float*>(base_ptr);  // [128][bn + 1] staging tile
-    const int ldt = g.bn + 1;
-    const int n_main = min(3, nkb);
-    for (int c0 = 0; c0 < g.bn; c0 += 32) {
-      uint32_t r[32];
-      float sum[32];
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      tmem_ld32(lane_addr + (uint32_t)(3 * g.bn), r);  // cross terms first (smallest magnitude)
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
-      for (int a = 0; a < n_main; ++a) {
-        tmem_ld32(lane_addr + (uint32_t)(a * g.bn), r);
+  } else {
+    // ---- epilogue warps: TMEM -> registers -> (+bias, ReLU, accumulate) -> global, straight from registers;
+    // the accumulators are released to the MMA warp as soon as the last column chunk has been read ----
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - EPI_THREAD0;
+    const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      TILE_DECODE(tile)
+      const uint32_t buf = lt % (uint32_t)g.nbuf, use = lt / (uint32_t)g.nbuf;
+      mbar_wait(tmem_full_bar(buf), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + q * 32 + lane;   // output row held by this thread
+      const bool row_ok = m < g.M;
+      float* crow = g.C + (size_t)tz_ * g.M * g.ldc + (size_t)(row_ok ? m : 0) * g.ldc;
+      const int n_main = min(3, nkb);
+      const uint32_t lane_addr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < g.bn; c0 += 32) {
+        uint32_t r0[32], r1[32];
+        float v[32];
+        tmem_ld32(lane_addr + (uint32_t)(3 * g.bn + c0), r0);  // cross terms (smallest magnitude first)
+        tmem_ld32(lane_addr + (uint32_t)c0, r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
-      }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        if (n_main > 1) {
+          tmem_ld32(lane_addr + (uint32_t)(g.bn + c0), r0);
+          if (n_main > 2) tmem_ld32(lane_addr + (uint32_t)(2 * g.bn + c0), r1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = sum[j];
-        const int n = n0 + c0 + j;
-        if (g.bias && n < g.N) v += g.bias[n];
-        if (g.relu) v = fmaxf(v, 0.f);
-        ct_s[row * ldt + c0 + j] = v;
-      }
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    float* C = g.C + (size_t)blockIdx.z * g.M * g.ldc;
-    const int ew = warp - 2;  // 0..3: rows ew*32 .. +31
-    for (int rr = 0; rr < 32; ++rr) {
-      const int rloc = ew * 32 + rr, m = m0 + rloc;
-      if (m >= g.M) break;
-      for (int c = lane; c < g.bn; c += 32) {
-        const int n = n0 + c;
-        if (n < g.N) {
-          float v = ct_s[rloc * ldt + c];
-          float* dst = C + (size_t)m * g.ldc + n;
-          if (g.accumulate) { v += *dst; ct_s[rloc * ldt + c] = v; }
-          *dst = v;
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r0[j]);
+          if (n_main > 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r1[j]);
+          }
+        }
+        if (c0 + 32 >= g.bn) {  // every column of this accumulator set is in registers: hand it back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        }
+        const int nb = n0 + c0;
+        if (g.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok) {
+          if (vec_ok) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const int n = nb + 4 * j4;
+              if (n + 3 < g.N) {
+                float4* dst = reinterpret_cast<float4*>(crow + n);
+                if (g.accumulate) {
+                  const float4 o = *dst;
+                  v[4 * j4] += o.x; v[4 * j4 + 1] += o.y; v[4 * j4 + 2] += o.z; v[4 * j4 + 3] += o.w;
+                }
+                *dst = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < g.N) {
+                    if (g.accumulate) v[4 * j4 + e] += crow[n + e];
+                    crow[n + e] = v[4 * j4 + e];
+                  }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < g.N) {
+                if (g.accumulate) v[j] += crow[nb + j];
+                crow[nb + j] = v[j];
+              }
+          }
+        }
+        if (g.stats) {  // per-column sum / sum of squares over this warp's 32 rows
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = row_ok ? v[j] : 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          const float s1 = warp_transpose_sum(v, lane);
+          const float s2 = warp_transpose_sum(sq, lane);
+          float* dst = sm_stats + ((c0 >> 5) * 4 + q) * 64;
+          dst[lane] = s1;
+          dst[32 + lane] = s2;
         }
       }
-    }
-    if (g.stats) {
-      if (g.accumulate) asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ct < g.bn && n0 + ct < g.N) {
-        const int rows = min(TBM, g.M - m0);
-        float s1 = 0.f, s2 = 0.f;
-        for (int rloc = 0; rloc < rows; ++rloc) {
-          const float v = ct_s[rloc * ldt + ct];
-          s1 += v;
-          s2 = fmaf(v, v, s2);
+      if (g.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < g.bn && n0 + et < g.N) {
+          const float* src = sm_stats + ((et >> 5) * 4) * 64 + (et & 31);
+          const float s1 = (src[0] + src[64]) + (src[128] + src[192]);
+          const float s2 = (src[32] + src[96]) + (src[160] + src[224]);
+          g.stats[((size_t)tm_ * 2) * g.N + n0 + et] = s1;
+          g.stats[((size_t)tm_ * 2 + 1) * g.N + n0 + et] = s2;
         }
-        g.stats[((size_t)blockIdx.y * 2) * g.N + n0 + ct] = s1;
-        g.stats[((size_t)blockIdx.y * 2 + 1) * g.N + n0 + ct] = s2;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }
-teardown:
+#undef TILE_DECODE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -407,6 +509,25 @@ int make_map(CUtensorMap* map, const float* ptr, long long inner, long long oute
   return 0;
 }
 
+template <int CONV>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcArgs g, int tiles_n, int tiles_m, int zs, cudaStream_t st,
+              const char* what) {
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  g.tiles_m = tiles_m;
+  g.tiles_n = tiles_n;
+  g.zs = zs;
+  g.nbuf = (4 * g.bn <= 256) ? 2 : 1;
+  const long long total = (long long)tiles_m * tiles_n * zs;
+  const int ctas = (int)(total < OCRS_NUM_SMS ? total : OCRS_NUM_SMS);
+  gemm_tc_kernel<CONV><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, g);
+  OCRS_CHECK_LAUNCH(what);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -424,11 +545,6 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
   OCRS_CHECK_ARG(ocrs_gemm_tc_supported(A, lda, B, ldb), "gemm_tc: operands must be 16-byte aligned with ld %% 4 == 0");
   OCRS_CHECK_ARG(splits >= 1, "gemm_tc: bad split count");
   OCRS_CHECK_ARG(splits == 1 || (!bias && !relu && !accumulate && !stats), "gemm_tc: split-K takes no epilogue");
-  static bool attr_set = false;
-  if (!attr_set) {
-    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   CUtensorMap ma, mb;
   if (a_kmajor) { if (make_map(&ma, A, K, M, lda, TBK, TBM, false)) return -1; }
@@ -442,10 +558,7 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
   // instruction descriptor: D = F32 (bit 4), A/B = TF32 (2 << 7, 2 << 10), majors, N >> 3 at 17, M >> 4 at 24
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
             ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-  dim3 grid(ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs);
-  gemm_tc_kernel<<<grid, 320, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
-  OCRS_CHECK_LAUNCH("gemm_tc_kernel");
-  return 0;
+  return launch_tc<0>(ma, mb, g, ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs, (cudaStream_t)stream, "gemm_tc_kernel");
 }
 
 // 3x3 / pad-1 / stride-1 convolution as an implicit GEMM on the tensor cores (no im2col buffer):
@@ -455,11 +568,6 @@ int ocrs_conv3x3_tc(const float* x, int N, int H, int W, int Cin, const float* w
                     long long ldc, const float* bias, int relu, float* stats, void* stream) {
   OCRS_CHECK_ARG(Cin % TBK == 0 && Cin > 0, "conv3x3_tc: Cin %d must be a multiple of 32", Cin);
   OCRS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)wp % 16 == 0), "conv3x3_tc: operands must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
-    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   const long long Ml = (long long)N * H * W;
   OCRS_CHECK_ARG(Ml < 2147483647LL - 128, "conv3x3_tc: too many pixels");
   const int M = (int)Ml, K = 9 * Cin;
@@ -469,10 +577,7 @@ int ocrs_conv3x3_tc(const float* x, int N, int H, int W, int Cin, const float* w
   if (make_map(&mb, wp, K, Cout, K, TBK, bn, false)) return -1;
   TcArgs g{out, ldc, M, Cout, K, bias, relu, 0, stats, K / TBK, 0, 0, bn, 0, 1, H, W, Cin};
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-  dim3 grid(ocrs_cdiv(Cout, bn), ocrs_cdiv(M, TBM), 1);
-  gemm_tc_kernel<<<grid, 320, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
-  OCRS_CHECK_LAUNCH("gemm_tc_kernel(conv3x3)");
-  return 0;
+  return launch_tc<1>(ma, mb, g, ocrs_cdiv(Cout, bn), ocrs_cdiv(M, TBM), 1, (cudaStream_t)stream, "gemm_tc_kernel(conv3x3)");
 }
 
 // Weight gradient of the same convolution, also without an im2col buffer:
@@ -483,11 +588,6 @@ int ocrs_conv3x3_wgrad_tc(const float* dy, const float* x, int N, int H, int W, 
   OCRS_CHECK_ARG(Cin % TBK == 0 && Cout % 4 == 0, "conv3x3_wgrad_tc: unsupported channel counts %d -> %d", Cin, Cout);
   OCRS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0), "conv3x3_wgrad_tc: operands must be 16-byte aligned");
   OCRS_CHECK_ARG(splits >= 1, "conv3x3_wgrad_tc: bad split count");
-  static bool attr_set = false;
-  if (!attr_set) {
-    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   const long long Kl = (long long)N * H * W;
   OCRS_CHECK_ARG(Kl < 2147483647LL - 128, "conv3x3_wgrad_tc: too many pixels");
   const int K = (int)Kl, Nn = 9 * Cin, bn = 128;
@@ -500,10 +600,8 @@ int ocrs_conv3x3_wgrad_tc(const float* dy, const float* x, int N, int H, int W, 
   const int zs = ocrs_cdiv(total_kb, g.kb_per_split);
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
             ((uint32_t)(TBM >> 4) << 24);
-  dim3 grid(ocrs_cdiv(Nn, bn), ocrs_cdiv(Cout, TBM), zs);
-  gemm_tc_kernel<<<grid, 320, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, g);
-  OCRS_CHECK_LAUNCH("gemm_tc_kernel(conv3x3 wgrad)");
-  return 0;
+  return launch_tc<2>(ma, mb, g, ocrs_cdiv(Nn, bn), ocrs_cdiv(Cout, TBM), zs, (cudaStream_t)stream,
+                      "gemm_tc_kernel(conv3x3 wgrad)");
 }
 
 // Number of [M][ldc] partial products ocrs_gemm_tc writes for a requested split count.
