@@ -317,6 +317,161 @@ bn_act_pool_bwd_apply_kernel(const float* __restrict__ y, PoolGeom g, const floa
   *reinterpret_cast<float4*>(dy + (((size_t)n * g.H + iy) * g.W + ix) * g.C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// ---- compile-time-window versions of the two kernels above (the windows the CRNN uses) ----
+// Everything lives in registers (the generic kernels index their window arrays dynamically and spill to
+// local memory), and the apply kernel walks pooling CELLS: one thread reads a window once and writes the
+// gradient of all its positions, instead of every position re-reading its whole window.
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* p) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  return F4{{q.x, q.y, q.z, q.w}};
+}
+__device__ __forceinline__ F4 ldg4(const float* p) {
+  const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+  return F4{{q.x, q.y, q.z, q.w}};
+}
+
+// Routed gradient of a full window for one channel: `am` = position that receives `gpass` (max), or -1 = every
+// position receives gpass (avg).
+template <int CNT, int MODE>
+__device__ __forceinline__ void route_static(const float (&v)[CNT], float s, float t, int relu, float g, int& am,
+                                             float& gpass) {
+  if (MODE == 1) { am = -1; gpass = g / (float)CNT; return; }
+  am = 0;
+  float pre = fmaf(v[0], s, t);
+  float m = relu ? fmaxf(pre, 0.f) : pre;
+#pragma unroll
+  for (int i = 1; i < CNT; ++i) {
+    const float pi = fmaf(v[i], s, t);
+    const float a = relu ? fmaxf(pi, 0.f) : pi;
+    if (a > m) { m = a; am = i; pre = pi; }
+  }
+  gpass = (!relu || pre > 0.f) ? g : 0.f;
+}
+
+template <int PH, int PW, int MODE>
+__global__ void __launch_bounds__(256)
+bn_act_pool_bwd_reduce_t(const float* __restrict__ y, PoolGeom g, const float* __restrict__ sc,
+                         const float* __restrict__ sh, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ dout,
+                         float* __restrict__ partials) {
+  extern __shared__ float red[];  // [256/C4][2][C]
+  constexpr int CNT = PH * PW;
+  const int C4 = g.C >> 2, lanes = 256 / C4;
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const long long npix = (long long)g.N * g.Hp * g.Wp;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  const F4 s = ldg4(sc + c4 * 4), t = ldg4(sh + c4 * 4), mu = ldg4(mean + c4 * 4), is = ldg4(invstd + c4 * 4);
+  const size_t rowC = (size_t)g.W * g.C;
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+    long long r = p;
+    const int ox = (int)(r % g.Wp);
+    r /= g.Wp;
+    const int oy = (int)(r % g.Hp), n = (int)(r / g.Hp);
+    const F4 gv = ld4(dout + (size_t)n * g.son + (size_t)oy * g.soh + (size_t)ox * g.sow + c4 * 4);
+    const float* y0 = y + (((size_t)n * g.H + oy * PH) * g.W + ox * PW) * g.C + c4 * 4;
+    F4 q[CNT];
+#pragma unroll
+    for (int dy = 0; dy < PH; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < PW; ++dx) q[dy * PW + dx] = ld4(y0 + dy * rowC + (size_t)dx * g.C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[CNT];
+#pragma unroll
+      for (int wi = 0; wi < CNT; ++wi) v[wi] = q[wi].v[j];
+      int am;
+      float gp;
+      route_static<CNT, MODE>(v, s.v[j], t.v[j], g.relu, gv.v[j], am, gp);
+      if (MODE == 1) {
+        float sv = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < CNT; ++wi) sv += v[wi];
+        a[j] += gp * (float)CNT;
+        b[j] = fmaf(gp, (sv - (float)CNT * mu.v[j]) * is.v[j], b[j]);
+      } else {
+        float vm = v[0];
+#pragma unroll
+        for (int wi = 1; wi < CNT; ++wi) vm = (wi == am) ? v[wi] : vm;
+        a[j] += gp;
+        b[j] = fmaf(gp, (vm - mu.v[j]) * is.v[j], b[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[(pl * 2) * g.C + c4 * 4 + j] = a[j];
+    red[(pl * 2 + 1) * g.C + c4 * 4 + j] = b[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.C; i += 256) {
+    float sum = 0.f;
+    for (int q2 = 0; q2 < lanes; ++q2) sum += red[q2 * 2 * g.C + i];
+    partials[(size_t)blockIdx.x * 2 * g.C + i] = sum;
+  }
+}
+
+// One thread per (sample, pooling cell, 4 channels); cells cover the whole input, the ragged border cells
+// (outside every window) get dz = 0.
+template <int PH, int PW, int MODE>
+__global__ void __launch_bounds__(256)
+bn_act_pool_bwd_apply_t(const float* __restrict__ y, PoolGeom g, const float* __restrict__ sc,
+                        const float* __restrict__ sh, const float* __restrict__ k1, const float* __restrict__ k2,
+                        const float* __restrict__ k3, const float* __restrict__ dout, float* __restrict__ dy) {
+  constexpr int CNT = PH * PW;
+  const int C4 = g.C >> 2;
+  const int Hc = (g.H + PH - 1) / PH, Wc = (g.W + PW - 1) / PW;
+  const long long total = (long long)g.N * Hc * Wc * C4;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  long long r = i / C4;
+  const int cx = (int)(r % Wc);
+  r /= Wc;
+  const int cy = (int)(r % Hc), n = (int)(r / Hc);
+  const bool full = cy < g.Hp && cx < g.Wp;
+  const size_t rowC = (size_t)g.W * g.C;
+  const size_t off0 = (((size_t)n * g.H + cy * PH) * g.W + cx * PW) * g.C + c4 * 4;
+  F4 q[CNT];
+  bool in[CNT];
+#pragma unroll
+  for (int dy_ = 0; dy_ < PH; ++dy_)
+#pragma unroll
+    for (int dx = 0; dx < PW; ++dx) {
+      const int wi = dy_ * PW + dx;
+      in[wi] = full || (cy * PH + dy_ < g.H && cx * PW + dx < g.W);
+      q[wi] = in[wi] ? ld4(y + off0 + dy_ * rowC + (size_t)dx * g.C) : F4{{0.f, 0.f, 0.f, 0.f}};
+    }
+  F4 gv{{0.f, 0.f, 0.f, 0.f}};
+  if (full) gv = ld4(dout + (size_t)n * g.son + (size_t)cy * g.soh + (size_t)cx * g.sow + c4 * 4);
+  const F4 s = ldg4(sc + c4 * 4), t = ldg4(sh + c4 * 4);
+  const F4 a1 = ldg4(k1 + c4 * 4), a2 = ldg4(k2 + c4 * 4), a3 = ldg4(k3 + c4 * 4);
+  F4 o[CNT];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[CNT];
+#pragma unroll
+    for (int wi = 0; wi < CNT; ++wi) v[wi] = q[wi].v[j];
+    int am = -2;
+    float gp = 0.f;
+    if (full) route_static<CNT, MODE>(v, s.v[j], t.v[j], g.relu, gv.v[j], am, gp);
+#pragma unroll
+    for (int wi = 0; wi < CNT; ++wi) {
+      const float dz = (am == -1 || am == wi) ? gp : 0.f;
+      o[wi].v[j] = fmaf(a1.v[j], dz, fmaf(a2.v[j], v[wi], a3.v[j]));
+    }
+  }
+#pragma unroll
+  for (int dy_ = 0; dy_ < PH; ++dy_)
+#pragma unroll
+    for (int dx = 0; dx < PW; ++dx) {
+      const int wi = dy_ * PW + dx;
+      if (in[wi])
+        *reinterpret_cast<float4*>(dy + off0 + dy_ * rowC + (size_t)dx * g.C) =
+            make_float4(o[wi].v[0], o[wi].v[1], o[wi].v[2], o[wi].v[3]);
+    }
+}
+
 // ReLU backward in place on a GEMM output that was stored post-ReLU: d *= (a > 0).
 __global__ void relu_bwd_kernel(const float* __restrict__ a, float* __restrict__ d, long long n4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,8 +692,15 @@ int ocrs_rec_bn_act_pool_bwd_reduce(const float* y, int N, int H, int W, int C, 
   const int lanes = 256 / (C / 4);
   const size_t smem = (size_t)lanes * 2 * C * sizeof(float);
   OCRS_CHECK_ARG(smem <= 48 * 1024, "bn_act_pool_bwd_reduce: smem");
-  bn_act_pool_bwd_reduce_kernel<<<ocrs_rec_pool_bwd_blocks(), 256, smem, (cudaStream_t)stream>>>(
-      y, g, sc, sh, mean, invstd, dout, partials);
+  const int blocks = ocrs_rec_pool_bwd_blocks();
+  cudaStream_t st = (cudaStream_t)stream;
+#define OCRS_POOL_REDUCE(PH_, PW_, MODE_) \
+  bn_act_pool_bwd_reduce_t<PH_, PW_, MODE_><<<blocks, 256, smem, st>>>(y, g, sc, sh, mean, invstd, dout, partials)
+  if (ph == 2 && pw == 2 && mode == 0) OCRS_POOL_REDUCE(2, 2, 0);
+  else if (ph == 2 && pw == 1 && mode == 0) OCRS_POOL_REDUCE(2, 1, 0);
+  else if (ph == 4 && pw == 1 && mode == 1) OCRS_POOL_REDUCE(4, 1, 1);
+  else bn_act_pool_bwd_reduce_kernel<<<blocks, 256, smem, st>>>(y, g, sc, sh, mean, invstd, dout, partials);
+#undef OCRS_POOL_REDUCE
   OCRS_CHECK_LAUNCH("bn_act_pool_bwd_reduce_kernel");
   return 0;
 }
@@ -550,8 +712,15 @@ int ocrs_rec_bn_act_pool_bwd_apply(const float* y, int N, int H, int W, int C, i
   PoolGeom g;
   if (make_geom(g, N, H, W, C, ph, pw, mode, relu, son, soh, sow)) return -1;
   const long long total = (long long)N * H * W * (C / 4);
-  bn_act_pool_bwd_apply_kernel<<<ocrs_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y, g, sc, sh, k1, k2, k3,
-                                                                                      dout, dy);
+  const long long cells = (long long)N * ocrs_cdiv(H, ph) * ocrs_cdiv(W, pw) * (C / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+#define OCRS_POOL_APPLY(PH_, PW_, MODE_) \
+  bn_act_pool_bwd_apply_t<PH_, PW_, MODE_><<<ocrs_cdiv(cells, 256), 256, 0, st>>>(y, g, sc, sh, k1, k2, k3, dout, dy)
+  if (ph == 2 && pw == 2 && mode == 0) OCRS_POOL_APPLY(2, 2, 0);
+  else if (ph == 2 && pw == 1 && mode == 0) OCRS_POOL_APPLY(2, 1, 0);
+  else if (ph == 4 && pw == 1 && mode == 1) OCRS_POOL_APPLY(4, 1, 1);
+  else bn_act_pool_bwd_apply_kernel<<<ocrs_cdiv(total, 256), 256, 0, st>>>(y, g, sc, sh, k1, k2, k3, dout, dy);
+#undef OCRS_POOL_APPLY
   OCRS_CHECK_LAUNCH("bn_act_pool_bwd_apply_kernel");
   return 0;
 }
