@@ -16,22 +16,56 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// out[k] = sum_b partials[b][k], accumulated in double in a fixed order (deterministic).
+// RL row lanes x 32 columns per block; four independent loads in flight per thread.
+template <int RL>
+__global__ void __launch_bounds__(32 * RL)
 finalize_partials_kernel(const float* __restrict__ partials, int nblk, int K, float* __restrict__ out) {
-  __shared__ double red[8][33];
+  __shared__ double red[RL][33];
   const int kx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + kx;
   double s = 0.0;
-  if (k < K)
-    for (int b = ry; b < nblk; b += 8) s += (double)partials[(size_t)b * K + k];
+  if (k < K) {
+    int b = ry;
+    for (; b + 3 * RL < nblk; b += 4 * RL) {
+      const float v0 = partials[(size_t)b * K + k], v1 = partials[(size_t)(b + RL) * K + k];
+      const float v2 = partials[(size_t)(b + 2 * RL) * K + k], v3 = partials[(size_t)(b + 3 * RL) * K + k];
+      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; b < nblk; b += RL) s += (double)partials[(size_t)b * K + k];
+  }
   red[ry][kx] = s;
   __syncthreads();
   if (ry == 0 && k < K) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += red[q][kx];
+    for (int q = 0; q < RL; ++q) t += red[q][kx];
     out[k] = (float)t;
   }
+}
+
+// Few rows, many columns (split-K GEMM partials): one thread per 4 columns, 16-byte loads, 4 rows in flight.
+__global__ void __launch_bounds__(128)
+finalize_partials4_kernel(const float* __restrict__ partials, int nblk, int K, float* __restrict__ out) {
+  const int k = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (k >= K) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int b = 0;
+  for (; b + 3 < nblk; b += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(partials + (size_t)b * K + k);
+    const float4 c = *reinterpret_cast<const float4*>(partials + (size_t)(b + 1) * K + k);
+    const float4 d = *reinterpret_cast<const float4*>(partials + (size_t)(b + 2) * K + k);
+    const float4 e = *reinterpret_cast<const float4*>(partials + (size_t)(b + 3) * K + k);
+    s0 += ((double)a.x + (double)c.x) + ((double)d.x + (double)e.x);
+    s1 += ((double)a.y + (double)c.y) + ((double)d.y + (double)e.y);
+    s2 += ((double)a.z + (double)c.z) + ((double)d.z + (double)e.z);
+    s3 += ((double)a.w + (double)c.w) + ((double)d.w + (double)e.w);
+  }
+  for (; b < nblk; ++b) {
+    const float4 a = *reinterpret_cast<const float4*>(partials + (size_t)b * K + k);
+    s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+  }
+  *reinterpret_cast<float4*>(out + k) = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -887,7 +921,14 @@ plane_sum_kernel(const float* __restrict__ v, long long v_ss, int C, long long H
 extern "C" {
 
 int ocrs_finalize_partials(const float* partials, int nblk, int K, float* out, void* stream) {
-  finalize_partials_kernel<<<ocrs_cdiv(K, 32), 256, 0, (cudaStream_t)stream>>>(partials, nblk, K, out);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool al = ((uintptr_t)partials % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (K % 4 == 0 && al && K >= 16384 && nblk <= 256)
+    finalize_partials4_kernel<<<ocrs_cdiv(K / 4, 128), 128, 0, st>>>(partials, nblk, K, out);
+  else if (nblk >= 256)
+    finalize_partials_kernel<32><<<ocrs_cdiv(K, 32), 1024, 0, st>>>(partials, nblk, K, out);
+  else
+    finalize_partials_kernel<8><<<ocrs_cdiv(K, 32), 256, 0, st>>>(partials, nblk, K, out);
   OCRS_CHECK_LAUNCH("finalize_partials_kernel");
   return 0;
 }

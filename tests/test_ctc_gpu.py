@@ -37,7 +37,8 @@ def test_golden_small(golden):
 
 @pytest.mark.parametrize(
     "T,N,C,S,ragged",
-    [(201, 64, 97, 40, False), (201, 64, 97, 64, True), (257, 16, 97, 64, True), (50, 5, 11, 1, True), (33, 7, 5, 16, True), (300, 3, 97, 120, True), (520, 2, 30, 255, False)],
+    [(201, 64, 97, 40, False), (201, 64, 97, 64, True), (257, 16, 97, 64, True), (50, 5, 11, 1, True), (33, 7, 5, 16, True), (300, 3, 97, 120, True), (520, 2, 30, 255, False),
+     (60, 4, 200, 20, True), (40, 3, 700, 10, True), (3, 2, 97, 1, False), (1, 2, 7, 1, True)],
 )
 def test_vs_oracle(T, N, C, S, ragged):
     g = torch.Generator().manual_seed(T * 1000 + N)
