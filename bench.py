@@ -181,7 +181,11 @@ def kernel_profile(wl: Workload, steps=2):
 
 # entry points that launch the same dominant kernel are judged together
 KERNEL_OF = {"ocrs_gemm_tc": "gemm_tc_kernel", "ocrs_conv3x3_tc": "gemm_tc_kernel", "ocrs_conv3x3_wgrad_tc": "gemm_tc_kernel",
-             "ocrs_gemm": "gemm_kernel"}
+             "ocrs_gemm_tc_presplit": "gemm_tc_kernel", "ocrs_conv3x3_tc_presplit": "gemm_tc_kernel",
+             "ocrs_gemm": "gemm_kernel", "ocrs_det_pw_wgrad": "pw_wgrad_mma_kernel", "ocrs_det_dwpw_fwd": "dwpw_fwd_kernel",
+             "ocrs_det_dw_bwd": "dw_bwd_kernel", "ocrs_det_pwT_bwd": "pwT_bwd_kernel",
+             "ocrs_bnrelu_bwd_reduce": "bnrelu_bwd_reduce_kernel", "ocrs_det_convt_wgrad": "convt_wgrad_mma_kernel",
+             "ocrs_gru_layer_fwd_persist": "gru_fwd_persist_kernel", "ocrs_gru_layer_bwd_persist": "gru_bwd_persist_kernel"}
 
 
 def measured_traffic(kernel):
@@ -216,6 +220,51 @@ def roofline(kind, prof, pk):
     ach = v["meta"] / (v["ms"] * 1e-3) / 1e9 if v["meta"] else None
     return dict(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=(ach / pk["hbm"]) if ach else None,
                 peak_source=pk["src"], **common)
+
+
+def ctc_saturating(device, pk, n=8192, reps=10):
+    """The CTC kernels at the HBM-saturating shape of SURVEY 8d (T=201, N=8192, C=97, S=40): algorithmic bytes
+    3*T*N*C*4 + 2*N*T*(2S+1)*4 over the CUDA-event time of forward + backward."""
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200._lib import call, ptr
+
+    T, C, S = 201, 97, 40
+    st = _lib.stream_ptr(device)
+    g = torch.Generator(device=device).manual_seed(0)
+    lp = torch.log_softmax(torch.randn(T, n, C, device=device, generator=g), 2)
+    tg = torch.randint(1, C, (n, 64), device=device, generator=g, dtype=torch.int32)
+    il = torch.full((n,), 200, dtype=torch.int32, device=device)
+    tl = torch.full((n,), S, dtype=torch.int32, device=device)
+    row = _lib.lib().ocrs_ctc_alpha_row(S)
+    alpha = torch.empty(n, T, row, device=device)
+    nll, loss, go = torch.empty(n, device=device), torch.empty((), device=device), torch.ones((), device=device)
+    grad = torch.empty_like(lp)
+
+    def fwd():
+        call("ocrs_ctc_fwd", ptr(lp), ptr(tg), 64, ptr(il), ptr(tl), T, n, C, S, 0, 1, 0, ptr(alpha), ptr(nll), ptr(loss), st)
+
+    def bwd():
+        call("ocrs_ctc_bwd", ptr(lp), ptr(tg), 64, ptr(il), ptr(tl), T, n, C, S, 0, 1, 0, ptr(alpha), ptr(nll), ptr(go), ptr(grad), st)
+
+    for _ in range(3):
+        fwd(), bwd()
+    torch.cuda.synchronize(device)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    for _ in range(reps):
+        fwd()
+    e[1].record()
+    for _ in range(reps):
+        bwd()
+    e[2].record()
+    torch.cuda.synchronize(device)
+    tf, tb = e[0].elapsed_time(e[1]) / reps, e[1].elapsed_time(e[2]) / reps
+    alg = 3 * T * n * C * 4 + 2 * n * T * (2 * S + 1) * 4
+    ach = alg / ((tf + tb) * 1e-3) / 1e9
+    tr = [measured_traffic(k) for k in ("ctc_alpha_kernel", "ctc_beta_grad_kernel")]
+    return dict(bound="hbm", kernel="ctc_alpha_kernel + ctc_beta_grad_kernel", shape=f"T={T} N={n} C={C} S={S}",
+                fwd_ms=tf, bwd_ms=tb, algorithmic_bytes=alg, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                peak_source=pk["src"], traffic=(sum(tr) if all(tr) else None))
 
 
 def cpu_reference_step(kind, n, threads):
@@ -311,6 +360,7 @@ def measure(kind, args, device, rank, world, dist_on, pk):
         res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         res["kernel_ms_total"] = round(tot, 3)
         if kind == "rec":
+            res["ctc_roofline"] = None  # filled below, after the workload's memory is released
             ach = REC_FLOP_PER_LINE * wl.units / (ms / args.steps * 1e-3) / 1e12
             res["step_roofline"] = dict(bound="tensor", achieved=ach, peak=pk["tf_sus"], unit="TFLOP/s", frac=ach / pk["tf_sus"])
         else:
@@ -319,6 +369,9 @@ def measure(kind, args, device, rank, world, dist_on, pk):
                                         note="algorithmic bytes of the ideally fused step at fp32 storage (SURVEY 8d)")
     del wl
     torch.cuda.empty_cache()
+    if rank == 0 and kind == "rec":
+        res["ctc_roofline"] = ctc_saturating(device, pk)
+        torch.cuda.empty_cache()
     return res
 
 
@@ -361,6 +414,7 @@ def main():
                        "precision_mode": "parity: fp32 storage; 3xTF32 tcgen05 GEMMs (4 TMEM accumulators) + fp32 FMA elsewhere"},
             "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
             "roofline": main_res.get("roofline"), "step_roofline": main_res.get("step_roofline"),
+            "ctc_roofline": main_res.get("ctc_roofline"),
             "kernel_ms_per_step": main_res.get("kernel_ms_per_step"),
         }
         if other_res is not None:

@@ -56,6 +56,9 @@ SIGNATURES: dict[str, list] = {
     "ocrs_gemm_tc_supported": [P, L, P, L],
     "ocrs_gemm_tc": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_gemm_tc_splits": [I, I],
+    "ocrs_gemm_tc_presplit": [P, L, I, P, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
+    "ocrs_conv3x3_tc_presplit": [P, I, I, I, I, P, P, I, P, L, P, I, P, P],
+    "ocrs_split_tf32": [P, P, P, L, P],
     "ocrs_conv3x3_tc": [P, I, I, I, I, P, I, P, L, P, I, P, P],
     "ocrs_conv3x3_wgrad_tc": [P, P, I, I, I, I, I, P, I, P],
     "ocrs_im2col_nhwc": [P, I, I, I, I, I, I, I, I, I, I, P, P],

@@ -50,6 +50,7 @@ struct TcArgs {
   int conv, cH, cW, cC;
   int tiles_m, tiles_n, zs;  // tile grid walked by the persistent CTAs
   int nbuf;                  // TMEM accumulator sets (2 when 4*bn <= 256 columns)
+  int b_split;               // B arrives pre-split (map_b = TF32-exact hi, map_b2 = lo): weights, split once per step
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,7 +135,8 @@ constexpr int EPI_THREAD0 = 320;
 // 4*bn <= 256 TMEM columns the accumulators are double-buffered and the drain is hidden completely.
 template <int CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_b2, TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -189,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         TILE_DECODE(tile)
-        uint32_t tx_bytes = A_TILE_BYTES + b_bytes;
+        uint32_t tx_bytes = A_TILE_BYTES + (g.b_split ? 2u : 1u) * b_bytes;
         if (CONV == 2) {
           int nvalid = 0;
           for (int c = 0; c < g.bn / 32; ++c) nvalid += (n0 + 32 * c < 9 * g.cC) ? 1 : 0;
@@ -217,9 +219,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tma_load_2d(sb + c * 4096, &map_b, ci0, k0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
               }
             }
-          } else if (!g.b_mn) tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
-          else
+          } else if (!g.b_mn) {
+            tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
+            if (g.b_split) tma_load_2d(sb + A_TILE_BYTES, &map_b2, k0, n0, full_bar(s));
+          } else {
             for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0, full_bar(s));
+            if (g.b_split)
+              for (int c = 0; c < g.bn / 32; ++c)
+                tma_load_2d(sb + A_TILE_BYTES + c * 4096, &map_b2, n0 + 32 * c, k0, full_bar(s));
+          }
         }
       }
     }
@@ -266,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // 8 warps (2 per scheduler). Each thread owns 4 float4 of A and 4 of B per stage; all eight are
     // loaded before any is stored so the shared-memory latency overlaps.
     const int ct = threadIdx.x - 64;  // 0..255
-    const int b_vec = (int)b_bytes / 16;
+    const int b_vec = g.b_split ? 0 : (int)b_bytes / 16;  // pre-split B tiles need no conversion
     auto split4 = [](const float4& v, float4& h, float4& l) {
       h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
       h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
@@ -509,9 +517,19 @@ int make_map(CUtensorMap* map, const float* ptr, long long inner, long long oute
   return 0;
 }
 
+// hi = v rounded to TF32 (the converter warps' rounding), lo = v - hi (exact).
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
 template <int CONV>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcArgs g, int tiles_n, int tiles_m, int zs, cudaStream_t st,
-              const char* what) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mb2, TcArgs g, int tiles_n, int tiles_m, int zs,
+              cudaStream_t st, const char* what) {
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -523,7 +541,8 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcArgs g, int tiles_
   g.nbuf = (4 * g.bn <= 256) ? 2 : 1;
   const long long total = (long long)tiles_m * tiles_n * zs;
   const int ctas = (int)(total < OCRS_NUM_SMS ? total : OCRS_NUM_SMS);
-  gemm_tc_kernel<CONV><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, g);
+  g.b_split = mb2 != nullptr;
+  gemm_tc_kernel<CONV><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
   OCRS_CHECK_LAUNCH(what);
   return 0;
 }
@@ -537,20 +556,24 @@ int ocrs_gemm_tc_supported(const float* A, long long lda, const float* B, long l
   return (lda % 4 == 0) && (ldb % 4 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
 }
 
-// Same contract as ocrs_gemm (gemm.cu): a_kmajor: A is [M][K] else [K][M]; b_kmajor: B is [N][K] else [K][N].
-int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor,
-                 float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate,
-                 float* stats, int splits, void* stream) {
+static int gemm_tc_impl(const float* A, long long lda, int a_kmajor, const float* B, const float* B_lo, long long ldb,
+                        int b_kmajor, float* C, long long ldc, int M, int N, int K, const float* bias, int relu,
+                        int accumulate, float* stats, int splits, void* stream) {
   OCRS_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tc: bad dims %d %d %d", M, N, K);
   OCRS_CHECK_ARG(ocrs_gemm_tc_supported(A, lda, B, ldb), "gemm_tc: operands must be 16-byte aligned with ld %% 4 == 0");
+  OCRS_CHECK_ARG(!B_lo || ((uintptr_t)B_lo % 16 == 0), "gemm_tc: B_lo must be 16-byte aligned");
   OCRS_CHECK_ARG(splits >= 1, "gemm_tc: bad split count");
   OCRS_CHECK_ARG(splits == 1 || (!bias && !relu && !accumulate && !stats), "gemm_tc: split-K takes no epilogue");
   const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mb2;
   if (a_kmajor) { if (make_map(&ma, A, K, M, lda, TBK, TBM, false)) return -1; }
   else          { if (make_map(&ma, A, M, K, lda, 32, TBK, true)) return -1; }
   if (b_kmajor) { if (make_map(&mb, B, K, N, ldb, TBK, bn, false)) return -1; }
   else          { if (make_map(&mb, B, N, K, ldb, 32, TBK, true)) return -1; }
+  if (B_lo) {
+    if (b_kmajor) { if (make_map(&mb2, B_lo, K, N, ldb, TBK, bn, false)) return -1; }
+    else          { if (make_map(&mb2, B_lo, N, K, ldb, 32, TBK, true)) return -1; }
+  }
   TcArgs g{C, ldc, M, N, K, bias, relu, accumulate, stats, 0, !a_kmajor, !b_kmajor, bn, 0, 0, 0, 0, 0};
   const int total_kb = ocrs_cdiv(K, TBK);
   g.kb_per_split = ocrs_cdiv(total_kb, splits);
@@ -558,7 +581,52 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
   // instruction descriptor: D = F32 (bit 4), A/B = TF32 (2 << 7, 2 << 10), majors, N >> 3 at 17, M >> 4 at 24
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
             ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-  return launch_tc<0>(ma, mb, g, ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs, (cudaStream_t)stream, "gemm_tc_kernel");
+  return launch_tc<0>(ma, mb, B_lo ? &mb2 : nullptr, g, ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), zs, (cudaStream_t)stream, "gemm_tc_kernel");
+}
+
+// Same contract as ocrs_gemm (gemm.cu): a_kmajor: A is [M][K] else [K][M]; b_kmajor: B is [N][K] else [K][N].
+int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor,
+                 float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate,
+                 float* stats, int splits, void* stream) {
+  return gemm_tc_impl(A, lda, a_kmajor, B, nullptr, ldb, b_kmajor, C, ldc, M, N, K, bias, relu, accumulate, stats, splits, stream);
+}
+
+// ocrs_gemm_tc with the B operand (a weight matrix) already split by ocrs_split_tf32 into B_hi / B_lo of the same
+// layout: both halves arrive by TMA and the converter warps only touch A (14% less shared-memory traffic per k-block).
+int ocrs_gemm_tc_presplit(const float* A, long long lda, int a_kmajor, const float* B_hi, const float* B_lo, long long ldb,
+                          int b_kmajor, float* C, long long ldc, int M, int N, int K, const float* bias, int relu,
+                          int accumulate, float* stats, int splits, void* stream) {
+  OCRS_CHECK_ARG(B_lo != nullptr, "gemm_tc_presplit: B_lo is null");
+  return gemm_tc_impl(A, lda, a_kmajor, B_hi, B_lo, ldb, b_kmajor, C, ldc, M, N, K, bias, relu, accumulate, stats, splits, stream);
+}
+
+// hi[i] = src[i] rounded to TF32, lo[i] = src[i] - hi[i]: the operand split of the 3xTF32 GEMM, done once per
+// step for weight matrices.
+int ocrs_split_tf32(const float* src, float* hi, float* lo, long long n, void* stream) {
+  OCRS_CHECK_ARG(n >= 0, "split_tf32: bad length");
+  if (n == 0) return 0;
+  split_tf32_kernel<<<ocrs_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(src, hi, lo, n);
+  OCRS_CHECK_LAUNCH("split_tf32_kernel");
+  return 0;
+}
+
+static int conv3x3_tc_impl(const float* x, int N, int H, int W, int Cin, const float* wp, const float* wp_lo, int Cout,
+                           float* out, long long ldc, const float* bias, int relu, float* stats, void* stream) {
+  OCRS_CHECK_ARG(Cin % TBK == 0 && Cin > 0, "conv3x3_tc: Cin %d must be a multiple of 32", Cin);
+  OCRS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)wp % 16 == 0) && ((uintptr_t)wp_lo % 16 == 0),
+                 "conv3x3_tc: operands must be 16-byte aligned");
+  const long long Ml = (long long)N * H * W;
+  OCRS_CHECK_ARG(Ml < 2147483647LL - 128, "conv3x3_tc: too many pixels");
+  const int M = (int)Ml, K = 9 * Cin;
+  const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+  CUtensorMap ma, mb, mb2;
+  if (make_map(&ma, x, Cin, M, Cin, TBK, TBM, false)) return -1;
+  if (make_map(&mb, wp, K, Cout, K, TBK, bn, false)) return -1;
+  if (wp_lo && make_map(&mb2, wp_lo, K, Cout, K, TBK, bn, false)) return -1;
+  TcArgs g{out, ldc, M, Cout, K, bias, relu, 0, stats, K / TBK, 0, 0, bn, 0, 1, H, W, Cin};
+  g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  return launch_tc<1>(ma, mb, wp_lo ? &mb2 : nullptr, g, ocrs_cdiv(Cout, bn), ocrs_cdiv(M, TBM), 1, (cudaStream_t)stream,
+                      "gemm_tc_kernel(conv3x3)");
 }
 
 // 3x3 / pad-1 / stride-1 convolution as an implicit GEMM on the tensor cores (no im2col buffer):
@@ -566,18 +634,14 @@ int ocrs_gemm_tc(const float* A, long long lda, int a_kmajor, const float* B, lo
 // Forward convolution and, with the flipped/transposed weights, the data gradient.
 int ocrs_conv3x3_tc(const float* x, int N, int H, int W, int Cin, const float* wp, int Cout, float* out,
                     long long ldc, const float* bias, int relu, float* stats, void* stream) {
-  OCRS_CHECK_ARG(Cin % TBK == 0 && Cin > 0, "conv3x3_tc: Cin %d must be a multiple of 32", Cin);
-  OCRS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)wp % 16 == 0), "conv3x3_tc: operands must be 16-byte aligned");
-  const long long Ml = (long long)N * H * W;
-  OCRS_CHECK_ARG(Ml < 2147483647LL - 128, "conv3x3_tc: too many pixels");
-  const int M = (int)Ml, K = 9 * Cin;
-  const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
-  CUtensorMap ma, mb;
-  if (make_map(&ma, x, Cin, M, Cin, TBK, TBM, false)) return -1;
-  if (make_map(&mb, wp, K, Cout, K, TBK, bn, false)) return -1;
-  TcArgs g{out, ldc, M, Cout, K, bias, relu, 0, stats, K / TBK, 0, 0, bn, 0, 1, H, W, Cin};
-  g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-  return launch_tc<1>(ma, mb, g, ocrs_cdiv(Cout, bn), ocrs_cdiv(M, TBM), 1, (cudaStream_t)stream, "gemm_tc_kernel(conv3x3)");
+  return conv3x3_tc_impl(x, N, H, W, Cin, wp, nullptr, Cout, out, ldc, bias, relu, stats, stream);
+}
+
+// ocrs_conv3x3_tc with the packed weights already split by ocrs_split_tf32 (wp_hi, wp_lo).
+int ocrs_conv3x3_tc_presplit(const float* x, int N, int H, int W, int Cin, const float* wp_hi, const float* wp_lo, int Cout,
+                             float* out, long long ldc, const float* bias, int relu, float* stats, void* stream) {
+  OCRS_CHECK_ARG(wp_lo != nullptr, "conv3x3_tc_presplit: wp_lo is null");
+  return conv3x3_tc_impl(x, N, H, W, Cin, wp_hi, wp_lo, Cout, out, ldc, bias, relu, stats, stream);
 }
 
 // Weight gradient of the same convolution, also without an im2col buffer:
@@ -600,7 +664,7 @@ int ocrs_conv3x3_wgrad_tc(const float* dy, const float* x, int N, int H, int W, 
   const int zs = ocrs_cdiv(total_kb, g.kb_per_split);
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
             ((uint32_t)(TBM >> 4) << 24);
-  return launch_tc<2>(ma, mb, g, ocrs_cdiv(Nn, bn), ocrs_cdiv(Cout, TBM), zs, (cudaStream_t)stream,
+  return launch_tc<2>(ma, mb, nullptr, g, ocrs_cdiv(Nn, bn), ocrs_cdiv(Cout, TBM), zs, (cudaStream_t)stream,
                       "gemm_tc_kernel(conv3x3 wgrad)");
 }
 

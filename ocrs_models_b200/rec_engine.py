@@ -29,14 +29,40 @@ EXACT_FWD = os.environ.get("OCRS_EXACT_FWD", "0") == "1"
 # Implicit-GEMM 3x3 convolutions (im2col folded into the TMA coordinates); OCRS_IMPLICIT=0 goes back to
 # an explicit im2col buffer + GEMM.
 IMPLICIT = os.environ.get("OCRS_IMPLICIT", "1") == "1"
+# Weight operands of the tensor-core GEMMs are split into TF32 hi/lo once per use in HBM (ocrs_split_tf32) and
+# both halves arrive by TMA, so the converter warps only touch the activation operand. OCRS_PRESPLIT=0 converts
+# the weights inside the GEMM like the activations.
+PRESPLIT = os.environ.get("OCRS_PRESPLIT", "1") == "1"
+
+
+class Split:
+    """A weight matrix split for the 3xTF32 GEMM: `hi` (TF32-exact) and `lo` (remainder), same layout."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, w, st):
+        w = w.detach().contiguous()
+        self.hi = torch.empty_like(w)
+        self.lo = torch.empty_like(w)
+        call("ocrs_split_tf32", ptr(w), ptr(self.hi), ptr(self.lo), w.numel(), st)
+
+
+def _maybe_split(w, st):
+    return Split(w, st) if (PRESPLIT and GEMM_BACKEND == "tc") else w
 
 
 def conv3x3(x, N, H, W, cin, wp, cout, st, bias=None, relu=False, stats=None):
     """3x3 / pad 1 convolution of an NHWC tensor on the tensor cores without an im2col buffer.
     wp: [cout, (ky, kx, ci)]. Returns [N*H*W, cout]."""
     out = _empty((N * H * W, cout), x.device)
-    call("ocrs_conv3x3_tc", ptr(x), N, H, W, cin, ptr(wp), cout, ptr(out), cout, ptr(bias), int(relu), ptr(stats), st,
-         meta=2.0 * N * H * W * cout * 9 * cin)
+    if isinstance(wp, torch.Tensor):
+        wp = _maybe_split(wp, st)
+    if isinstance(wp, Split):
+        call("ocrs_conv3x3_tc_presplit", ptr(x), N, H, W, cin, ptr(wp.hi), ptr(wp.lo), cout, ptr(out), cout, ptr(bias),
+             int(relu), ptr(stats), st, meta=2.0 * N * H * W * cout * 9 * cin)
+    else:
+        call("ocrs_conv3x3_tc", ptr(x), N, H, W, cin, ptr(wp), cout, ptr(out), cout, ptr(bias), int(relu), ptr(stats), st,
+             meta=2.0 * N * H * W * cout * 9 * cin)
     return out
 
 
@@ -66,7 +92,7 @@ def _empty(shape, dev):
 
 
 def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bias=None, relu=False,
-         accumulate=False, stats=None, split_ok=False, exact=False):
+         accumulate=False, stats=None, split_ok=False, exact=False, b_weight=False):
     """C[M,N] = op(A) op(B). A/B are tensors or raw pointers. With `split_ok` the reduction is split
     over K when the output has too few tiles to fill the GPU. `exact` forces the fp32-FMA kernel:
     outputs that feed ReLU / max-pool decisions must be accurate to ~1e-6, because a perturbation d
@@ -74,6 +100,9 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bi
     an A/B switch: the 4-accumulator 3xTF32 tensor-core kernel reaches the same accuracy."""
     dev = out.device if out is not None else (A.device if isinstance(A, torch.Tensor) else None)
     pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
+    b_lo = None
+    if isinstance(B, Split):
+        b_lo, B = B.lo, B.hi
     pb = B.data_ptr() if isinstance(B, torch.Tensor) else B
     if out is None:
         out = _empty((M, N), dev)
@@ -88,7 +117,15 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bi
         tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
         want = max(1, min(TARGET_BLOCKS // tiles, K // 256))
         splits = (lib.ocrs_gemm_tc_splits if tc else lib.ocrs_gemm_splits)(K, want)
-    if splits == 1:
+    if b_weight and tc and PRESPLIT and splits == 1 and b_lo is None and isinstance(B, torch.Tensor):
+        sp = Split(B, st)  # B is a weight matrix: split it once in HBM instead of per tile in the GEMM
+        pb, b_lo = sp.hi.data_ptr(), sp.lo
+    if b_lo is not None and not tc:
+        raise RuntimeError("pre-split weights need the tensor-core GEMM")
+    if splits == 1 and b_lo is not None:
+        call("ocrs_gemm_tc_presplit", pa, lda, int(a_kmajor), pb, ptr(b_lo), ldb, int(b_kmajor), ptr(out), ldc, M, N, K,
+             ptr(bias), int(relu), int(accumulate), ptr(stats), 1, st, meta=2.0 * M * N * K)
+    elif splits == 1:
         call(fn, pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(out), ldc, M, N, K, ptr(bias),
              int(relu), int(accumulate), ptr(stats), 1, st, meta=2.0 * M * N * K)
     else:
@@ -198,7 +235,7 @@ class _RecFunction(torch.autograd.Function):
                     rows = lib.ocrs_gemm_stat_rows(M)
                     stats = _empty((rows, 2, cout), dev) if training else None
                     y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1],
-                             st, stats=stats, exact=EXACT_FWD)
+                             st, stats=stats, exact=EXACT_FWD, b_weight=True)
                 bs = _bn_finalize(bn, stats, rows, M, training, relu, st, dev)
                 Hp, Wp = Ho // ph, Wo // pw
                 if out is None:
@@ -216,7 +253,7 @@ class _RecFunction(torch.autograd.Function):
                 col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, 3, 3, 1, 1, st)
                 M = N * Ho * Wo
                 a = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, conv.out_channels,
-                         col.shape[1], st, bias=conv.bias, relu=True, exact=EXACT_FWD)
+                         col.shape[1], st, bias=conv.bias, relu=True, exact=EXACT_FWD, b_weight=True)
                 return a, dict(col=col, inp=inp, a=a, inp_geom=(Hh, Ww, cin))
 
             a3, H3, W3, rec["3"] = conv_bn_pool(a0, H1, W1, 32, cv["3"], cv["4"], 2, 2, 0, True)
@@ -242,7 +279,7 @@ class _RecFunction(torch.autograd.Function):
                 for sfx in ("", "_reverse"):
                     w_ih = getattr(gru, f"weight_ih_l{layer}{sfx}")
                     b_ih = getattr(gru, f"bias_ih_l{layer}{sfx}")
-                    gi.append(gemm(layer_in, isz, True, w_ih, isz, True, TN, 768, isz, st, bias=b_ih))
+                    gi.append(gemm(layer_in, isz, True, w_ih, isz, True, TN, 768, isz, st, bias=b_ih, b_weight=True))
                 out = _empty((T, N, 512), dev)
                 gates = _empty((T, N, 2, 4, 256), dev)
                 call("ocrs_gru_layer_fwd_persist" if GRU_BACKEND == "persist" else "ocrs_gru_layer_fwd",
@@ -253,7 +290,7 @@ class _RecFunction(torch.autograd.Function):
                 layer_in = out
             lin = model.output[0]
             C = lin.out_features
-            logits = gemm(layer_in, 512, True, lin.weight, 512, True, TN, C, 512, st, bias=lin.bias)
+            logits = gemm(layer_in, 512, True, lin.weight, 512, True, TN, C, 512, st, bias=lin.bias, b_weight=True)
             lp = _empty((T, N, C), dev)
             call("ocrs_log_softmax_fwd", ptr(logits), ptr(lp), TN, C, st)
         if save:
@@ -281,7 +318,7 @@ class _RecFunction(torch.autograd.Function):
             out1 = gru_rec[1]["out"]
             grads[id(lin.weight)] = gemm(dlog, C, False, out1, 512, False, C, 512, TN, st, split_ok=True)
             grads[id(lin.bias)] = colsum(dlog, C, TN, C, st, dev)
-            d_out = gemm(dlog, C, True, lin.weight, 512, False, TN, 512, C, st)
+            d_out = gemm(dlog, C, True, lin.weight, 512, False, TN, 512, C, st, b_weight=True)
             for layer in (1, 0):
                 r = gru_rec[layer]
                 isz, xin, out, gates = r["isz"], r["x"], r["out"], r["gates"]
@@ -320,7 +357,7 @@ class _RecFunction(torch.autograd.Function):
                     else:
                         dwhh = torch.zeros((768, 256), device=dev)
                     grads[id(getattr(gru, "weight_hh_" + nm))] = dwhh
-                    gemm(dgi[d], 768, True, w_ih, isz, False, TN, isz, 768, st, out=d_in, accumulate=(d == 1))
+                    gemm(dgi[d], 768, True, w_ih, isz, False, TN, isz, 768, st, out=d_in, accumulate=(d == 1), b_weight=True)
                 d_out = d_in
             d_seq = d_out  # [T, N, 128]
 
@@ -363,7 +400,7 @@ class _RecFunction(torch.autograd.Function):
                 dcol, Hi, Wi = im2col(dy, N, Ho, Wo, cout, kh, kh, kh - 1 - pad, kh - 1 - pad, st)
                 assert (Hi, Wi) == (Hh, Ww)
                 return gemm(dcol, dcol.shape[1], True, _w_dgrad(conv.weight), dcol.shape[1], True, N * Hh * Ww, cin,
-                            dcol.shape[1], st)
+                            dcol.shape[1], st, b_weight=True)
 
             r = rec["19"]
             dy, Ho, Wo = bn_pool_bwd(r, cv["19"], cv["20"], d_seq, r["ostr"])

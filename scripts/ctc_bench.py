@@ -1,6 +1,7 @@
 """CTC kernel at the HBM-saturating shape of SURVEY 8d (N=8192, T=201, C=97, S=40)."""
-import sys, torch
+import json, os, sys, torch
 sys.path.insert(0, '.')
+PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
 from ocrs_models_b200 import _lib
 from ocrs_models_b200._lib import call, ptr
 dev = torch.device("cuda:0")
@@ -26,4 +27,4 @@ for N in (64, 1024, 8192):
     e[2].record(); torch.cuda.synchronize()
     tf, tb = e[0].elapsed_time(e[1]) / 10, e[1].elapsed_time(e[2]) / 10
     bytes_alg = 3 * T * N * C * 4 + 2 * N * T * (2 * S + 1) * 4
-    print(f"N={N}: fwd {tf:.3f} ms bwd {tb:.3f} ms  algorithmic {bytes_alg/1e9:.3f} GB -> {bytes_alg/1e9/((tf+tb)*1e-3):.0f} GB/s ({bytes_alg/1e9/((tf+tb)*1e-3)/6451.2*100:.1f}% of measured HBM peak)")
+    print(f"N={N}: fwd {tf:.3f} ms bwd {tb:.3f} ms  algorithmic {bytes_alg/1e9:.3f} GB -> {bytes_alg/1e9/((tf+tb)*1e-3):.0f} GB/s ({bytes_alg/1e9/((tf+tb)*1e-3)/PEAK*100:.1f}% of measured HBM peak)")

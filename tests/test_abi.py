@@ -62,7 +62,9 @@ def test_no_torch_types_cross_the_boundary():
 
 def test_host_side_queries_need_no_gpu(lib):
     assert lib.ocrs_version() >= 100
-    assert lib.ocrs_ctc_alpha_row(40) == 96 and lib.ocrs_ctc_alpha_row(255) == 512 and lib.ocrs_ctc_alpha_row(256) == 0
+    # alpha rows hold (blank, label) pairs, NP per lane: 2 * NP * ceil((S + 1) / NP) floats
+    assert lib.ocrs_ctc_alpha_row(40) == 84 and lib.ocrs_ctc_alpha_row(255) == 512 and lib.ocrs_ctc_alpha_row(256) == 0
+    assert lib.ocrs_ctc_alpha_row(0) == 2 and lib.ocrs_ctc_alpha_row(31) == 64 and lib.ocrs_ctc_alpha_row(63) == 128
     assert lib.ocrs_det_dwpw_partial_rows(2, 64, 64) == 2 * 2 * 2
     assert lib.ocrs_gemm_splits(1152, 4) == 4
     assert lib.ocrs_gemm_tc_splits(1152, 5) in (4, 5)

@@ -44,6 +44,41 @@ def test_gemm_layouts(M, N, K, ak, bk, backend, monkeypatch):
     assert rel_l2(out, ref) < tol
 
 
+@pytest.mark.parametrize("M,N,K,bk", [(300, 97, 512, True), (1000, 64, 288, True), (640, 768, 128, True), (500, 128, 768, False)])
+def test_gemm_presplit_weights_bit_exact(M, N, K, bk, monkeypatch):
+    """B (a weight matrix) split once in HBM by ocrs_split_tf32 must give the very same bits as the in-kernel
+    conversion: the split kernel and the converter warps use the same rounding."""
+    from ocrs_models_b200 import rec_engine
+    from ocrs_models_b200.rec_engine import Split, gemm
+
+    monkeypatch.setattr(rec_engine, "PRESPLIT", False)  # plain tensors -> in-kernel conversion (the reference here)
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g)
+    Bd = (B if bk else B.t().contiguous()).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    sp = Split(Bd, _st())
+    assert torch.equal(sp.hi + sp.lo, Bd) and torch.equal(sp.hi.view(torch.int32) & 0x1FFF, torch.zeros_like(sp.hi, dtype=torch.int32))
+    ref = gemm(A, K, True, Bd, Bd.shape[1], bk, M, N, K, _st(), bias=bias, relu=True)
+    out = gemm(A, K, True, sp, Bd.shape[1], bk, M, N, K, _st(), bias=bias, relu=True)
+    assert torch.equal(out, ref)
+    assert rel_l2(out, torch.relu(A.double().cpu() @ B.double().t() + bias.double().cpu())) < 3e-6
+
+
+def test_conv3x3_presplit_weights_bit_exact(monkeypatch):
+    from ocrs_models_b200 import rec_engine
+    from ocrs_models_b200.rec_engine import Split, _w_fwd, conv3x3
+
+    monkeypatch.setattr(rec_engine, "PRESPLIT", False)
+    g = torch.Generator().manual_seed(11)
+    N, H, W, cin, cout = 2, 16, 200, 64, 128
+    x = torch.randn(N, H, W, cin, generator=g).cuda()
+    wp = _w_fwd((torch.randn(cout, cin, 3, 3, generator=g) * 0.1).cuda())
+    ref = conv3x3(x, N, H, W, cin, wp, cout, _st())
+    out = conv3x3(x, N, H, W, cin, Split(wp, _st()), cout, _st())
+    assert torch.equal(out, ref)
+
+
 @pytest.mark.parametrize("backend", ["tc", "simt"])
 def test_gemm_column_stats(backend, monkeypatch):
     from ocrs_models_b200 import _lib, rec_engine
