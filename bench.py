@@ -44,10 +44,12 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -341,7 +343,7 @@ def measure(kind, args, device, rank, world, dist_on, pk):
         wl.step_resident()
     torch.cuda.synchronize(device)
     l0 = lib.ocrs_launch_count()
-    with ClockSampler(device.index or 0) as cs:
+    with ClockSampler(device.index or 0, enabled=not args.no_clocks) as cs:
         ms, _ = timed(wl.step_resident, args.steps, 0, device, dist_on)
     launches = lib.ocrs_launch_count() - l0
     _, wall = timed(wl.step_e2e, args.steps, 1, device, dist_on)
@@ -384,6 +386,8 @@ def main():
     ap.add_argument("--workload", default="rec", choices=["rec", "det"], help="headline workload of the JSON line")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other workload's sub-object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true",
+                    help="do not start the nvidia-smi clock sampler (for runs under ncu, which follows child processes)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
