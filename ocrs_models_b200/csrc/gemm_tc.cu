@@ -9,15 +9,20 @@
 // to the fourth; the epilogue adds them in round-to-nearest fp32. Error ~5e-7 at K = 1152, on par
 // with an fp32 FMA loop.
 //
-// One CTA per 128 x BN output tile (BN in {32, 64, 128}), 320 threads:
-//   warp 0      TMA producer: fp32 operand tiles -> 128B-swizzled shared memory (3 stages)
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, accumulator in TMEM)
-//   warps 2-9   split each landed stage into hi / lo tiles in place; warps 2-5 then run the epilogue:
-//               tcgen05.ld TMEM -> registers -> (+bias, ReLU) -> smem tile -> coalesced global
-//               stores (+ per-column sum / sum^2 partials for a following BatchNorm)
+// Persistent CTAs (min(#tiles, 148)) of 448 threads walk 128 x BN output tiles (BN in {32, 64, 128}):
+//   warp 0        TMA producer: fp32 operand tiles -> 128B-swizzled shared memory (3 stages); weight operands may
+//                 arrive already split (hi and lo tiles both by TMA, ocrs_split_tf32)
+//   warp 1        TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, accumulators in TMEM)
+//   warps 2-9     converters: split each landed stage into hi / lo tiles in place (fence.proxy.async)
+//   warps 10-13   epilogue: tcgen05.ld TMEM -> registers -> (+bias, ReLU, C +=) -> 16-byte global stores straight
+//                 from registers (+ per-column sum / sum^2 partials for a following BatchNorm); the accumulators go
+//                 back to the MMA warp as soon as they are in registers, so the next tile's main loop overlaps
+//                 the stores (and the whole drain when the accumulators are double-buffered, 4*BN <= 256 columns)
+// Measured (profiles/): the main loop is bound by the shared-memory port - converter LDS/STS, TMA writes and the
+// UMMA operand reads of the 12 MMAs per k-block share 128 B/clk - not by the tensor pipe (56% active on conv.9).
 // Operands may be K-major (X[rows][K]) or MN-major (X[K][rows]); the latter is what the weight
 // gradients dW = dY^T . X need, and is expressed purely through the TMA boxes and the UMMA
-// shared-memory descriptors (no transposes in HBM). Split-K over gridDim.z.
+// shared-memory descriptors (no transposes in HBM). Split-K slices are extra tiles of the same walk.
 #include "common.cuh"
 #include <cuda.h>
 

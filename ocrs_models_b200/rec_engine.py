@@ -8,12 +8,12 @@ hand-written BPTT / dgrad / wgrad kernels.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 from ._lib import call, ptr
-
-import os
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
