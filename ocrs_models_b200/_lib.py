@@ -37,7 +37,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_outconv_bwd": [P, P, P, L, I, I, I, I, P, P, P, P, P, L, P, P],
     "ocrs_reduce_rows": [I, L],
     "ocrs_bnrelu_bwd_reduce": [P, L, P, L, I, I, L, P, P, P, P, P, P, P],
-    "ocrs_bn_bwd_finalize": [P, I, I, D, P, P, P, P, P, P, P, P, P],
+    "ocrs_bn_bwd_finalize": [P, I, I, D, P, P, P, P, P, P, P, P, I, P],
     "ocrs_det_pwT_bwd": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, I, P, L, P],
     "ocrs_det_pw_wgrad_workers": [I, I, I],
     "ocrs_det_pw_wgrad": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, L, I, P, P, P, P, P, P],
@@ -148,6 +148,23 @@ def call(name: str, *args, meta=None) -> None:
 def ptr(t) -> int | None:
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def check_module_tensors(model, device, what: str) -> None:
+    """The kernels take raw pointers: every parameter and buffer must be a contiguous fp32 (int64 for
+    num_batches_tracked) CUDA tensor on the input's device. Anything else (model left on the CPU or another GPU,
+    .half()/.bfloat16(), channels_last) raises here instead of faulting inside a kernel."""
+    import torch
+
+    for kind, items in (("parameter", model.named_parameters()), ("buffer", model.named_buffers())):
+        for name, t in items:
+            if t.device != device:
+                raise RuntimeError(f"{what}: {kind} {name} is on {t.device} but the input is on {device} "
+                                   "(there is no CPU path: move the model with .to(device))")
+            if t.is_floating_point() and t.dtype != torch.float32:
+                raise RuntimeError(f"{what}: {kind} {name} has dtype {t.dtype}; the kernels compute in float32")
+            if not t.is_contiguous():
+                raise RuntimeError(f"{what}: {kind} {name} is not contiguous (memory_format / strided views are not supported)")
 
 
 def stream_ptr(device=None) -> int:

@@ -139,7 +139,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
                                        const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ k1,
-                                       float* __restrict__ k2, float* __restrict__ k3) {
+                                       float* __restrict__ k2, float* __restrict__ k3, int training) {
   __shared__ double red[2][32];
   const int c = blockIdx.x;
   double a = 0.0, b = 0.0;
@@ -157,10 +157,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
   dbeta[c] = (float)a;
   dgamma[c] = (float)b;
   const double is = invstd[c], g1 = (double)gamma[c] * is;
-  const double g2 = -g1 * is * b / count;
+  // eval-mode BatchNorm normalises with constants (the running statistics): dy = gamma * invstd * dz only
+  const double g2 = training ? -g1 * is * b / count : 0.0;
   k1[c] = (float)g1;
   k2[c] = (float)g2;
-  k3[c] = (float)(-g1 * a / count - g2 * (double)mean[c]);
+  k3[c] = training ? (float)(-g1 * a / count - g2 * (double)mean[c]) : 0.f;
 }
 
 struct DyCoef {  // everything needed to rebuild dy[co] from (d_a, y) on the fly
@@ -961,9 +962,9 @@ int ocrs_bnrelu_bwd_reduce(const float* d_a, long long da_ss, const float* y, lo
 
 int ocrs_bn_bwd_finalize(const float* partials, int nblk, int C, double count, const float* gamma,
                          const float* mean, const float* invstd, float* dgamma, float* dbeta,
-                         float* k1, float* k2, float* k3, void* stream) {
+                         float* k1, float* k2, float* k3, int training, void* stream) {
   bn_bwd_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(partials, nblk, C, count, gamma, mean,
-                                                              invstd, dgamma, dbeta, k1, k2, k3);
+                                                              invstd, dgamma, dbeta, k1, k2, k3, training);
   OCRS_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   return 0;
 }

@@ -535,11 +535,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restri
 template <int CONV>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mb2, TcArgs g, int tiles_n, int tiles_m, int zs,
               cudaStream_t st, const char* what) {
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // per device/context attribute, set on every call (cheap, thread-safe, correct with several GPUs per process)
+  OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   g.tiles_m = tiles_m;
   g.tiles_n = tiles_n;
   g.zs = zs;

@@ -85,13 +85,13 @@ class _Sep:
             bn.num_batches_tracked.add_(1)
         y.xf = xf_dst
         if save is not None:
-            save[id(self)] = (inp, y, stats)
+            save[id(self)] = (inp, y, stats, bool(training))
         return y
 
     def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False):
         """d_a: gradient w.r.t. this block's activated output. Writes the gradient w.r.t. the
         block's (activated) input into `dx`; returns [d_wdw, d_wpw, d_gamma, d_beta]."""
-        inp, y, stats = saved.pop(id(self))
+        inp, y, stats, training = saved.pop(id(self))
         dev = y.t.device
         lib = _lib.lib()
         H, W, HW = y.H, y.W, y.H * y.W
@@ -103,7 +103,7 @@ class _Sep:
              ptr(stats[1]), ptr(part), st, meta=4.0 * N * HW * 2 * co)
         coef = torch.empty((5, co), dtype=torch.float32, device=dev)  # dgamma, dbeta, k1, k2, k3
         call("ocrs_bn_bwd_finalize", ptr(part), rows, co, float(N * HW), ptr(self.bn.weight), ptr(stats[0]),
-             ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), st)
+             ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), int(training), st)
         k = (ysc, ysh, ylo, ptr(coef[2]), ptr(coef[3]), ptr(coef[4]))
         g = new_view(N, ci, H, W, dev)
         call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
@@ -318,5 +318,6 @@ def detection_forward(model, x: torch.Tensor) -> torch.Tensor:
     if plan is None:
         plan = _Plan(model)
         model.__dict__["_plan"] = plan
+    _lib.check_module_tensors(model, x.device, "DetectionModel")
     x = x.float().contiguous()
     return _DetFunction.apply(plan, x, *plan.all_params())

@@ -297,14 +297,14 @@ class _RecFunction(torch.autograd.Function):
             ctx.model = model
             ctx.rec = rec
             ctx.gru_rec = gru_rec
-            ctx.misc = (x, a0, lp, N, H, W, T, C)
+            ctx.misc = (x, a0, lp, N, H, W, T, C, bool(training))
         return lp
 
     @staticmethod
     def backward(ctx, g_lp):
         model = ctx.model
         rec, gru_rec = ctx.rec, ctx.gru_rec
-        x, a0, lp, N, H, W, T, C = ctx.misc
+        x, a0, lp, N, H, W, T, C, training = ctx.misc
         dev = lp.device
         st = _lib.stream_ptr(dev)
         lib = _lib.lib()
@@ -370,7 +370,7 @@ class _RecFunction(torch.autograd.Function):
                      ptr(bs.shift), ptr(bs.mean), ptr(bs.invstd), ptr(dout), *dstr, ptr(part), st)
                 coef = _empty((5, cout), dev)
                 call("ocrs_bn_bwd_finalize", ptr(part), blocks, cout, float(N * Ho * Wo), ptr(bn.weight), ptr(bs.mean),
-                     ptr(bs.invstd), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), st)
+                     ptr(bs.invstd), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), int(training), st)
                 grads[id(bn.weight)] = coef[0].clone()
                 grads[id(bn.bias)] = coef[1].clone()
                 dy = _empty((N, Ho, Wo, cout), dev)
@@ -441,5 +441,10 @@ def recognition_forward(model, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError(f"expected (N, 1, 64, W) input, got {tuple(x.shape)}")
     if x.shape[3] < 4:
         raise RuntimeError("input width must be at least 4")
+    if x.requires_grad and torch.is_grad_enabled():
+        # conv.0's backward kernel produces weight/bias gradients only; refuse rather than return a silent zero
+        raise RuntimeError("ocrs_models_b200.RecognitionModel does not compute the gradient w.r.t. the input image "
+                           "(x.requires_grad must be False)")
+    _lib.check_module_tensors(model, x.device, "RecognitionModel")
     x = x.float().contiguous()
     return _RecFunction.apply(model, x, *model.parameters())

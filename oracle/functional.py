@@ -265,8 +265,10 @@ def param_names(sd: dict) -> list[str]:
     return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
 
 
-def train_step_grads(kind: str, sd: dict, batch: dict, dtype=torch.float32):
-    """fwd + loss + bwd of one training step on CPU. Returns (output, loss, grads, new_buffers)."""
+def train_step_grads(kind: str, sd: dict, batch: dict, dtype=torch.float32, training: bool = True):
+    """fwd + loss + bwd of one training step on CPU. Returns (output, loss, grads, new_buffers).
+    `training=False`: model.eval() forward (running BatchNorm statistics) with autograd still on, as the
+    reference's test() loops and frozen-BN fine-tuning do."""
     p = {}
     for k, v in sd.items():
         if v.is_floating_point():
@@ -276,10 +278,10 @@ def train_step_grads(kind: str, sd: dict, batch: dict, dtype=torch.float32):
         p[k] = v
     nb: dict = {}
     if kind == "det":
-        out = det_forward(p, batch["image"].to(dtype), True, nb)
+        out = det_forward(p, batch["image"].to(dtype), training, nb)
         loss = balanced_cross_entropy_loss(out, batch["mask"].to(dtype))
     else:
-        out = rec_forward(p, batch["image"].to(dtype), True, nb)
+        out = rec_forward(p, batch["image"].to(dtype), training, nb)
         loss = ctc_loss(out, batch["targets"], batch["input_lengths"], batch["target_lengths"])
     names = param_names(sd)
     gs = torch.autograd.grad(loss, [p[k] for k in names])

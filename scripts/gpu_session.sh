@@ -11,7 +11,7 @@ mkdir -p $O
 NCU="ncu --clock-control none --profile-from-start off --target-processes application-only"
 for s in $STAGES; do case $s in
 tests)
-  timeout -s KILL 240 python -m pytest tests -m gpu -q --durations=8 2>&1 | tail -25 > $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log ;;
+  timeout -s KILL 900 python -m pytest tests -m gpu -q -s --durations=8 2>&1 | grep -v "^Training\|it/s\|s/it" | tail -60 > $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log ;;
 bench)
   timeout -s KILL 300 python bench.py > $O/bench.json 2> $O/bench.err; cat $O/bench.json; tail -3 $O/bench.err ;;
 steps)

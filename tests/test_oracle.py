@@ -137,3 +137,16 @@ def test_adam_and_clip_restatement():
         assert abs(n - n_ref) < 1e-5
         for k in p:
             torch.testing.assert_close(p[k], ref[k].detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_bench_first_step_constants_present():
+    """bench.py asserts its first-step losses against these reference-derived constants (oracle/bench_constants.py)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    c = json.load(open(os.path.join(GOLDEN, "bench_first_step.json")))
+    assert np.isfinite([c["rec_loss_f64"], c["det_loss_f64"]]).all()
+    assert abs(c["rec_loss_f32"] - c["rec_loss_f64"]) < 1e-4 * c["rec_loss_f64"]
+    assert abs(c["det_loss_f32"] - c["det_loss_f64"]) < 1e-4 * c["det_loss_f64"]
