@@ -1,0 +1,512 @@
+// TMA-pipelined kernels of the detection U-Net's DepthwiseConv blocks (reference ocrs_models/models.py:7-28 and
+// its autograd). Same math and HBM layout as det_fwd.cu / det_bwd.cu (planar NCHW fp32 views, BatchNorm+ReLU
+// folded into the consumer's load), different data movement:
+//
+//   * persistent CTAs (<= 2 per SM) walk 32x32-pixel tiles; the haloed input tile of a channel chunk is ONE
+//     cp.async.bulk.tensor (TMA) box {40, 34, chunk} over a 4-D (W, H, C, N) tensor map - the hardware zero-fills
+//     the halo outside the image - landing in a 4-stage shared-memory ring guarded by mbarriers, so the loads of
+//     the next tiles are in flight while the current one is computed (the old kernels did load -> sync -> compute).
+//     The box starts at x0-4, not x0-1: the innermost TMA coordinate must be a multiple of 16 bytes (measured:
+//     UTMALDG raises "illegal instruction" otherwise, scripts/probe/tma_probe.cu);
+//   * a warp owns 4 rows x 32 consecutive pixels, a thread one column of 4 pixels: conflict-free 4-byte
+//     shared-memory reads, 128-byte coalesced global stores per warp instruction;
+//   * per-channel statistics (BatchNorm partial sums, weight-gradient partial sums) stay in registers across all
+//     the tiles of a CTA and are written once per CTA: partial rows = CTAs, reduced in double by finalize_partials
+//     (deterministic, no atomics);
+//   * the BatchNorm-backward reduction of the UPSTREAM block (sum dz, sum dz*yhat) is produced by the kernel that
+//     writes that block's d_a (the depthwise backward kernel here), instead of a separate pass over d_a and y.
+//
+// TMA needs 16-byte aligned bases and row strides: W % 4 == 0 (ocrs_det_tma_supported); other shapes (e.g. the
+// 75x37 level of the 800x600 training size) keep using det_fwd.cu / det_bwd.cu.
+#include "common.cuh"
+#include "tma_util.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int TW = 32, TH = 32;       // interior tile
+constexpr int BW = 40, BH = 34;       // haloed box: x0-4 .. x0+35, y0-1 .. y0+32 (tile column j = image column x0-4+j)
+constexpr int PLANE = BW * BH;        // 1360 floats per channel plane of a box
+constexpr int PPT = 4;                // rows per thread
+constexpr int NSTAGE = 4;
+constexpr int NTHREADS = 256;
+// shared-memory floats of a box of `ch` planes, padded so that the next TMA destination stays 128-byte aligned
+constexpr int box_floats(int ch) { return (ch * PLANE + 31) / 32 * 32; }
+
+// Sum over the 32 lanes of v[j] for all j at once; lane l returns the total of column (l % NV).
+template <int NV>
+__device__ __forceinline__ float warp_colsum(float (&v)[NV], int lane) {
+#pragma unroll
+  for (int o = NV / 2; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float send = up ? v[j] : v[j + o];
+      const float keep = up ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = NV; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
+struct TileWalk {  // spatial tiles (n, ty, tx) assigned round-robin to the CTAs of one channel group
+  int tiles_x, tiles_y, sp_total, sp0, sp_stride;
+  __device__ __forceinline__ int count() const { return sp0 < sp_total ? (sp_total - sp0 + sp_stride - 1) / sp_stride : 0; }
+  __device__ __forceinline__ void decode(int k, int& n, int& x0, int& y0) const {
+    const int sp = sp0 + k * sp_stride;
+    const int per = tiles_x * tiles_y;
+    n = sp / per;
+    const int r = sp - n * per;
+    y0 = (r / tiles_x) * TH;
+    x0 = (r % tiles_x) * TW;
+  }
+};
+
+// Load the 6x3 window (tile rows 4w..4w+5, tile columns lane+3..lane+5) of one channel plane, apply the producer's
+// BatchNorm+ReLU transform and zero what lies outside the image (padding applies AFTER activation).
+template <bool XF, bool BORDER>
+__device__ __forceinline__ void load_window(const float* t, float sc, float sh, float lo, const bool (&rowok)[PPT + 2],
+                                            const bool (&colok)[3], float (&v)[PPT + 2][3]) {
+#pragma unroll
+  for (int rr = 0; rr < PPT + 2; ++rr)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[rr][k] = t[rr * BW + k];
+  if (XF) {
+#pragma unroll
+    for (int rr = 0; rr < PPT + 2; ++rr)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        v[rr][k] = xform_apply(v[rr][k], sc, sh, lo);
+        if (BORDER) v[rr][k] = (rowok[rr] && colok[k]) ? v[rr][k] : 0.f;
+      }
+  }
+}
+
+// Per-thread validity of its window rows / columns for a tile at (x0, y0); returns whether the tile touches the border.
+__device__ __forceinline__ bool tile_masks(int x0, int y0, int H, int W, int lane, int warp, bool (&rowok)[PPT + 2],
+                                           bool (&colok)[3]) {
+  const bool border = x0 == 0 || y0 == 0 || x0 + TW + 1 > W || y0 + TH + 1 > H;  // uniform per CTA
+#pragma unroll
+  for (int rr = 0; rr < PPT + 2; ++rr) { const int gy = y0 - 1 + PPT * warp + rr; rowok[rr] = gy >= 0 && gy < H; }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { const int gx = x0 - 1 + lane + q; colok[q] = gx >= 0 && gx < W; }
+  return border;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward: y = pw1x1(dw3x3(xform(x))) + per-CTA BatchNorm partial sums (models.py:11-22).
+struct FwdArgs {
+  int Cin, Cout, H, W, N, n_cot;
+  const float *in_scale, *in_shift, *in_lo, *wdw, *wpw;
+  float* y; long long y_ss;
+  float* partials;  // [gridDim.x / n_cot][2][Cout] or null
+  TileWalk walk;    // sp0 / sp_stride filled per CTA
+};
+
+template <int CO_T, int FCH>
+__global__ void __launch_bounds__(NTHREADS, 2)
+sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE_FLOATS = box_floats(FCH);
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NSTAGE * STAGE_FLOATS);  // 64 bytes reserved
+  float* sdw = stages + NSTAGE * STAGE_FLOATS + 16;    // [Cin][12] (9 taps padded to 12 for 16-byte reads)
+  float* spw = sdw + a.Cin * 12;                       // [Cin][CO_T]
+  float* sred = spw + a.Cin * CO_T;                    // [8][2*CO_T]
+  float* sxf = sred + 8 * 2 * CO_T;                    // [3][Cin]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cot = blockIdx.x % a.n_cot, co0 = cot * CO_T;
+  TileWalk walk = a.walk;
+  walk.sp0 = blockIdx.x / a.n_cot;
+  walk.sp_stride = gridDim.x / a.n_cot;
+  const int Cin = a.Cin;
+  const bool has_xf = a.in_scale != nullptr;
+
+  for (int i = tid; i < Cin * 12; i += NTHREADS) {
+    const int c = i / 12, k = i - c * 12;
+    sdw[i] = k < 9 ? a.wdw[(size_t)c * 9 + k] : 0.f;
+  }
+  for (int i = tid; i < Cin * CO_T; i += NTHREADS) {
+    const int c = i / CO_T, o = i - c * CO_T;
+    spw[i] = (co0 + o < a.Cout) ? a.wpw[(size_t)(co0 + o) * Cin + c] : 0.f;
+  }
+  if (has_xf)
+    for (int i = tid; i < Cin; i += NTHREADS) { sxf[i] = a.in_scale[i]; sxf[Cin + i] = a.in_shift[i]; sxf[2 * Cin + i] = a.in_lo[i]; }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) tma::mbar_init(tma::smem_u32(&bars[s]), 1);
+    tma::fence_barrier_init();
+    tma::prefetch_map(&xmap);
+  }
+  __syncthreads();
+
+  const int nchunks = (Cin + FCH - 1) / FCH;
+  const int total = walk.count() * nchunks;
+  auto issue = [&](int j) {
+    const int k = j / nchunks, ch = j - k * nchunks;
+    int n, x0, y0;
+    walk.decode(k, n, x0, y0);
+    const uint32_t bar = tma::smem_u32(&bars[j % NSTAGE]);
+    tma::mbar_expect_tx(bar, FCH * PLANE * 4);  // the box's bytes (zero-filled halo included), not the padded stage
+    tma::load_4d(tma::smem_u32(stages + (j % NSTAGE) * STAGE_FLOATS), &xmap, x0 - 4, y0 - 1, ch * FCH, n, bar);
+  };
+  if (tid == 0)
+    for (int j = 0; j < NSTAGE && j < total; ++j) issue(j);
+
+  float acc[PPT][CO_T];
+  float stat = 0.f;  // lane l accumulates column l of (sum[0..CO_T), sumsq[0..CO_T)) over all tiles of this CTA
+  bool rowok[PPT + 2], colok[3];
+  bool border = false;
+  int n = 0, x0 = 0, y0 = 0;
+  int k = 0, ch = 0;
+  for (int j = 0; j < total; ++j) {
+    if (ch == 0) {
+      walk.decode(k, n, x0, y0);
+#pragma unroll
+      for (int i = 0; i < PPT; ++i)
+#pragma unroll
+        for (int o = 0; o < CO_T; ++o) acc[i][o] = 0.f;
+      border = tile_masks(x0, y0, a.H, a.W, lane, warp, rowok, colok);
+    }
+    const int s = j % NSTAGE;
+    tma::mbar_wait(tma::smem_u32(&bars[s]), (j / NSTAGE) & 1);
+    const float* st = stages + s * STAGE_FLOATS + (PPT * warp) * BW + lane + 3;
+    const int c0 = ch * FCH;
+    const int nc = min(FCH, Cin - c0);
+    for (int c = 0; c < nc; ++c) {
+      float v[PPT + 2][3];
+      const int ci = c0 + c;
+      const float sc = has_xf ? sxf[ci] : 1.f, sh = has_xf ? sxf[Cin + ci] : 0.f, lo = has_xf ? sxf[2 * Cin + ci] : 0.f;
+      if (!has_xf) load_window<false, false>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
+      else if (border) load_window<true, true>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
+      else load_window<true, false>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
+      const float4 w0 = *reinterpret_cast<const float4*>(sdw + ci * 12);
+      const float4 w1 = *reinterpret_cast<const float4*>(sdw + ci * 12 + 4);
+      const float w8 = sdw[ci * 12 + 8];
+      float d[PPT];
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        float t = v[i][0] * w0.x;
+        t = fmaf(v[i][1], w0.y, t); t = fmaf(v[i][2], w0.z, t);
+        t = fmaf(v[i + 1][0], w0.w, t); t = fmaf(v[i + 1][1], w1.x, t); t = fmaf(v[i + 1][2], w1.y, t);
+        t = fmaf(v[i + 2][0], w1.z, t); t = fmaf(v[i + 2][1], w1.w, t); t = fmaf(v[i + 2][2], w8, t);
+        d[i] = t;
+      }
+      const float4* w4 = reinterpret_cast<const float4*>(spw + ci * CO_T);
+#pragma unroll
+      for (int o4 = 0; o4 < CO_T / 4; ++o4) {
+        const float4 wv = w4[o4];
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          acc[i][o4 * 4 + 0] = fmaf(d[i], wv.x, acc[i][o4 * 4 + 0]);
+          acc[i][o4 * 4 + 1] = fmaf(d[i], wv.y, acc[i][o4 * 4 + 1]);
+          acc[i][o4 * 4 + 2] = fmaf(d[i], wv.z, acc[i][o4 * 4 + 2]);
+          acc[i][o4 * 4 + 3] = fmaf(d[i], wv.w, acc[i][o4 * 4 + 3]);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (tid == 0 && j + NSTAGE < total) issue(j + NSTAGE);
+    if (++ch == nchunks) {
+      ch = 0;
+      ++k;
+      const int gx = x0 + lane, gy0 = y0 + PPT * warp;
+      float sv[2 * CO_T];
+#pragma unroll
+      for (int o = 0; o < CO_T; ++o) {
+        float s1 = 0.f, s2 = 0.f;
+        float* yp = a.y + (size_t)n * a.y_ss + ((size_t)(co0 + o) * a.H + gy0) * a.W + gx;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          if (gx < a.W && gy0 + i < a.H) {
+            s1 += acc[i][o];
+            s2 = fmaf(acc[i][o], acc[i][o], s2);
+            if (co0 + o < a.Cout) yp[(size_t)i * a.W] = acc[i][o];
+          }
+        }
+        sv[o] = s1;
+        sv[CO_T + o] = s2;
+      }
+      if (a.partials) stat += warp_colsum<2 * CO_T>(sv, lane);
+    }
+  }
+  if (a.partials) {
+    if (lane < 2 * CO_T) sred[warp * 2 * CO_T + lane] = stat;
+    __syncthreads();
+    if (tid < 2 * CO_T) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sred[w * 2 * CO_T + tid];
+      const int which = tid / CO_T, o = tid - which * CO_T;
+      if (co0 + o < a.Cout)
+        a.partials[((size_t)(blockIdx.x / a.n_cot) * 2 + which) * a.Cout + co0 + o] = s;
+    }
+  }
+}
+
+template <int CO_T, int FCH>
+size_t fwd_smem(int Cin) {
+  return (size_t)NSTAGE * box_floats(FCH) * 4 + 64 + (size_t)Cin * (12 + CO_T + 3) * 4 + 8 * 2 * CO_T * 4 + 128;
+}
+
+int fwd_ctas(int N, int H, int W, int n_cot) {
+  const long long sp = (long long)N * ocrs_cdiv(W, TW) * ocrs_cdiv(H, TH);
+  long long per = (2 * OCRS_NUM_SMS) / n_cot;
+  if (per < 1) per = 1;
+  return (int)(sp < per ? sp : per);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Depthwise 3x3 backward (per channel): dx = corr(g, flip(w)) [+= old dx], dWdw[k] = sum g * xact(shifted),
+// and - for the block that PRODUCED x - the BatchNorm-backward sums over this kernel's output d_a = dx:
+//   sum dz, sum dz * (x - mean) * invstd   with   dz = dx * [xform(x) > lo].
+// CTA = (channel pair, subset of the spatial tiles): all per-channel sums live in registers for the whole kernel.
+struct DwBwdArgs {
+  int C, H, W, N, accumulate, ctas_per_chunk;
+  const float *isc, *ish, *ilo, *wdw;
+  const float *up_mean, *up_invstd;  // upstream BatchNorm statistics (null: no fused reduction)
+  float* dx; long long dx_ss;
+  float* wpart;    // [ctas_per_chunk][C][9]
+  float* bnpart;   // [ctas_per_chunk][2][C] or null
+  TileWalk walk;
+};
+constexpr int DCH = 2;  // channels per stage (g and x boxes of both)
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+sep_dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap xmap, DwBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int XOFF = box_floats(DCH);
+  constexpr int STAGE_FLOATS = 2 * XOFF;  // [g: DCH planes][x: DCH planes]
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NSTAGE * STAGE_FLOATS);  // 64 bytes reserved
+  float* sred = stages + NSTAGE * STAGE_FLOATS + 16;  // [8][DCH * 11]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = blockIdx.x / a.ctas_per_chunk, c0 = chunk * DCH;
+  TileWalk walk = a.walk;
+  walk.sp0 = blockIdx.x % a.ctas_per_chunk;
+  walk.sp_stride = a.ctas_per_chunk;
+  const bool has_xf = a.isc != nullptr;
+  const bool need_bn = a.bnpart != nullptr;
+
+  float w[DCH][9], sc[DCH], sh[DCH], lo[DCH], mu[DCH], is[DCH];
+#pragma unroll
+  for (int c = 0; c < DCH; ++c) {
+    const bool v = c0 + c < a.C;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) w[c][q] = v ? a.wdw[(size_t)(c0 + c) * 9 + q] : 0.f;
+    sc[c] = (v && has_xf) ? a.isc[c0 + c] : 1.f;
+    sh[c] = (v && has_xf) ? a.ish[c0 + c] : 0.f;
+    lo[c] = (v && has_xf) ? a.ilo[c0 + c] : -INFINITY;
+    mu[c] = (v && need_bn) ? a.up_mean[c0 + c] : 0.f;
+    is[c] = (v && need_bn) ? a.up_invstd[c0 + c] : 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) tma::mbar_init(tma::smem_u32(&bars[s]), 1);
+    tma::fence_barrier_init();
+    tma::prefetch_map(&gmap);
+    tma::prefetch_map(&xmap);
+  }
+  __syncthreads();
+  const int total = walk.count();
+  auto issue = [&](int j) {
+    int n, x0, y0;
+    walk.decode(j, n, x0, y0);
+    const uint32_t bar = tma::smem_u32(&bars[j % NSTAGE]);
+    float* dst = stages + (j % NSTAGE) * STAGE_FLOATS;
+    tma::mbar_expect_tx(bar, 2 * DCH * PLANE * 4);
+    tma::load_4d(tma::smem_u32(dst), &gmap, x0 - 4, y0 - 1, c0, n, bar);
+    tma::load_4d(tma::smem_u32(dst + XOFF), &xmap, x0 - 4, y0 - 1, c0, n, bar);
+  };
+  if (tid == 0)
+    for (int j = 0; j < NSTAGE && j < total; ++j) issue(j);
+
+  float dwacc[DCH][9], bn1[DCH], bn2[DCH];
+#pragma unroll
+  for (int c = 0; c < DCH; ++c) {
+    bn1[c] = 0.f; bn2[c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) dwacc[c][q] = 0.f;
+  }
+  for (int j = 0; j < total; ++j) {
+    int n, x0, y0;
+    walk.decode(j, n, x0, y0);
+    const int gx = x0 + lane, gy0 = y0 + PPT * warp;
+    const bool xok = gx < a.W;
+    // previous contents of dx (skip connections: two consumers accumulate): issue the loads before waiting
+    float old[DCH][PPT];
+#pragma unroll
+    for (int c = 0; c < DCH; ++c)
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        old[c][i] = 0.f;
+        if (a.accumulate && xok && gy0 + i < a.H && c0 + c < a.C)
+          old[c][i] = a.dx[(size_t)n * a.dx_ss + ((size_t)(c0 + c) * a.H + gy0 + i) * a.W + gx];
+      }
+    bool rowok[PPT + 2], colok[3];
+    const bool border = tile_masks(x0, y0, a.H, a.W, lane, warp, rowok, colok);
+    const int s = j % NSTAGE;
+    tma::mbar_wait(tma::smem_u32(&bars[s]), (j / NSTAGE) & 1);
+    const float* st = stages + s * STAGE_FLOATS + (PPT * warp) * BW + lane + 3;
+#pragma unroll
+    for (int c = 0; c < DCH; ++c) {
+      if (c0 + c >= a.C) continue;
+      float gv[PPT + 2][3], xv[PPT + 2][3];
+      load_window<false, false>(st + c * PLANE, 1.f, 0.f, 0.f, rowok, colok, gv);  // g is zero outside the image (TMA fill)
+      if (border) load_window<true, true>(st + XOFF + c * PLANE, sc[c], sh[c], lo[c], rowok, colok, xv);
+      else load_window<true, false>(st + XOFF + c * PLANE, sc[c], sh[c], lo[c], rowok, colok, xv);
+      float* dxp = a.dx + (size_t)n * a.dx_ss + ((size_t)(c0 + c) * a.H + gy0) * a.W + gx;
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        // dx[p] = sum_k w[k] * g[p - (k - 1)]: window element (i + 2 - ky, 2 - kx)
+        float t = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) t = fmaf(w[c][ky * 3 + kx], gv[i + 2 - ky][2 - kx], t);
+        if (xok && gy0 + i < a.H) {
+          const float gc = gv[i + 1][1];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) dwacc[c][ky * 3 + kx] = fmaf(gc, xv[i + ky][kx], dwacc[c][ky * 3 + kx]);
+          const float o = t + old[c][i];
+          dxp[(size_t)i * a.W] = o;
+          if (need_bn) {
+            const float raw = st[XOFF + c * PLANE + (i + 1) * BW + 1];  // xv holds the activated value
+            const float dz = (fmaf(raw, sc[c], sh[c]) > lo[c]) ? o : 0.f;
+            bn1[c] += dz;
+            bn2[c] = fmaf(dz, (raw - mu[c]) * is[c], bn2[c]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && j + NSTAGE < total) issue(j + NSTAGE);
+  }
+  // CTA reduction of the per-thread sums: DCH * (9 + 2) values
+#pragma unroll
+  for (int c = 0; c < DCH; ++c) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const float v = warp_sum(dwacc[c][q]);
+      if (lane == 0) sred[warp * DCH * 11 + c * 11 + q] = v;
+    }
+    const float v1 = warp_sum(bn1[c]), v2 = warp_sum(bn2[c]);
+    if (lane == 0) { sred[warp * DCH * 11 + c * 11 + 9] = v1; sred[warp * DCH * 11 + c * 11 + 10] = v2; }
+  }
+  __syncthreads();
+  if (tid < DCH * 11) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += sred[wv * DCH * 11 + tid];
+    const int c = tid / 11, q = tid - c * 11;
+    const int row = blockIdx.x % a.ctas_per_chunk;
+    if (c0 + c < a.C) {
+      if (q < 9) a.wpart[((size_t)row * a.C + c0 + c) * 9 + q] = s;
+      else if (need_bn) a.bnpart[((size_t)row * 2 + (q - 9)) * a.C + c0 + c] = s;
+    }
+  }
+}
+
+int dw_ctas_per_chunk(int N, int H, int W, int C) {
+  const long long sp = (long long)N * ocrs_cdiv(W, TW) * ocrs_cdiv(H, TH);
+  const int chunks = ocrs_cdiv(C, DCH);
+  long long per = (2 * OCRS_NUM_SMS + chunks - 1) / chunks;
+  if (per < 1) per = 1;
+  return (int)(sp < per ? sp : per);
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 when the TMA-pipelined DepthwiseConv kernels can run on these views (16-byte aligned planes, W % 4 == 0).
+int ocrs_det_tma_supported(const float* x, long long x_ss, const float* y, long long y_ss, int H, int W) {
+  return ocrs_plane_tma_ok(x, x_ss, H, W) && ocrs_plane_tma_ok(y, y_ss, H, W) && H >= 8 && W >= 8;
+}
+
+// Rows of the [rows][2][Cout] statistics partials ocrs_det_sep_fwd writes.
+int ocrs_det_sep_fwd_rows(int N, int H, int W, int Cout) {
+  return fwd_ctas(N, H, W, ocrs_cdiv(Cout, Cout <= 8 ? 8 : 16));
+}
+
+// DepthwiseConv block body (reference models.py:11-22), TMA-pipelined: y = pw1x1(dw3x3(xform(x))) and the
+// BatchNorm partial sums of y. Same contract as ocrs_det_dwpw_fwd except for the partial-row count.
+int ocrs_det_sep_fwd(const float* x, long long x_ss, int N, int Cin, int H, int W, const float* in_scale,
+                     const float* in_shift, const float* in_lo, const float* wdw, const float* wpw, int Cout,
+                     float* y, long long y_ss, float* partials, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "sep_fwd: bad dims");
+  OCRS_CHECK_ARG(ocrs_det_tma_supported(x, x_ss, y, y_ss, H, W), "sep_fwd: views are not TMA-addressable");
+  const int cot = Cout <= 8 ? 8 : 16;
+  FwdArgs a;
+  a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.N = N; a.n_cot = ocrs_cdiv(Cout, cot);
+  a.in_scale = in_scale; a.in_shift = in_shift; a.in_lo = in_lo; a.wdw = wdw; a.wpw = wpw;
+  a.y = y; a.y_ss = y_ss; a.partials = partials;
+  a.walk.tiles_x = ocrs_cdiv(W, TW); a.walk.tiles_y = ocrs_cdiv(H, TH);
+  a.walk.sp_total = N * a.walk.tiles_x * a.walk.tiles_y; a.walk.sp0 = 0; a.walk.sp_stride = 1;
+  const int ctas = fwd_ctas(N, H, W, a.n_cot) * a.n_cot;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap xmap;
+  if (Cin < 4) {
+    if (ocrs_plane_map(&xmap, x, x_ss, N, Cin, H, W, BW, BH, 1)) return -1;
+    const size_t smem = fwd_smem<8, 1>(Cin);
+    if (cot == 8) {
+      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sep_fwd_tma_kernel<8, 1><<<ctas, NTHREADS, smem, st>>>(xmap, a);
+    } else {
+      const size_t smem16 = fwd_smem<16, 1>(Cin);
+      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      sep_fwd_tma_kernel<16, 1><<<ctas, NTHREADS, smem16, st>>>(xmap, a);
+    }
+  } else {
+    if (ocrs_plane_map(&xmap, x, x_ss, N, Cin, H, W, BW, BH, 4)) return -1;
+    if (cot == 8) {
+      const size_t smem = fwd_smem<8, 4>(Cin);
+      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sep_fwd_tma_kernel<8, 4><<<ctas, NTHREADS, smem, st>>>(xmap, a);
+    } else {
+      const size_t smem = fwd_smem<16, 4>(Cin);
+      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sep_fwd_tma_kernel<16, 4><<<ctas, NTHREADS, smem, st>>>(xmap, a);
+    }
+  }
+  OCRS_CHECK_LAUNCH("sep_fwd_tma_kernel");
+  return 0;
+}
+
+// Rows of the [rows][C][9] weight-gradient partials (and [rows][2][C] BatchNorm partials) of ocrs_det_sep_dw_bwd.
+int ocrs_det_sep_dw_bwd_rows(int N, int H, int W, int C) { return dw_ctas_per_chunk(N, H, W, C); }
+
+// Depthwise 3x3 backward, TMA-pipelined: dx (+= when accumulate) and the dw weight-gradient partials, like
+// ocrs_det_dw_bwd; when up_mean/up_invstd/bn_partials are given it also emits the BatchNorm-backward sums
+// (sum dz, sum dz*yhat) of the block that produced x, computed from the final dx (replaces a separate
+// ocrs_bnrelu_bwd_reduce pass over d_a and y of that block).
+int ocrs_det_sep_dw_bwd(const float* g, long long g_ss, const float* x, long long x_ss, int N, int C, int H, int W,
+                        const float* isc, const float* ish, const float* ilo, const float* wdw, float* dx,
+                        long long dx_ss, int accumulate, float* w_partials, const float* up_mean,
+                        const float* up_invstd, float* bn_partials, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "sep_dw_bwd: bad dims");
+  OCRS_CHECK_ARG(ocrs_det_tma_supported(g, g_ss, x, x_ss, H, W) && ocrs_plane_tma_ok(dx, dx_ss, H, W),
+                 "sep_dw_bwd: views are not TMA-addressable");
+  OCRS_CHECK_ARG(bn_partials == nullptr || (up_mean && up_invstd && isc), "sep_dw_bwd: fused BN reduction needs the upstream statistics");
+  DwBwdArgs a;
+  a.C = C; a.H = H; a.W = W; a.N = N; a.accumulate = accumulate;
+  a.ctas_per_chunk = dw_ctas_per_chunk(N, H, W, C);
+  a.isc = isc; a.ish = ish; a.ilo = ilo; a.wdw = wdw; a.up_mean = up_mean; a.up_invstd = up_invstd;
+  a.dx = dx; a.dx_ss = dx_ss; a.wpart = w_partials; a.bnpart = bn_partials;
+  a.walk.tiles_x = ocrs_cdiv(W, TW); a.walk.tiles_y = ocrs_cdiv(H, TH);
+  a.walk.sp_total = N * a.walk.tiles_x * a.walk.tiles_y; a.walk.sp0 = 0; a.walk.sp_stride = 1;
+  CUtensorMap gmap, xmap;
+  if (ocrs_plane_map(&gmap, g, g_ss, N, C, H, W, BW, BH, DCH)) return -1;
+  if (ocrs_plane_map(&xmap, x, x_ss, N, C, H, W, BW, BH, DCH)) return -1;
+  const size_t smem = (size_t)NSTAGE * 2 * box_floats(DCH) * 4 + 64 + 8 * DCH * 11 * 4 + 128;
+  OCRS_CUDA(cudaFuncSetAttribute(sep_dw_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ctas = a.ctas_per_chunk * ocrs_cdiv(C, DCH);
+  sep_dw_bwd_tma_kernel<<<ctas, NTHREADS, smem, (cudaStream_t)stream>>>(gmap, xmap, a);
+  OCRS_CHECK_LAUNCH("sep_dw_bwd_tma_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -10,12 +10,17 @@ Follows reference ``DetectionModel.forward`` (ocrs_models/models.py:131-143) op 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 from ._lib import call, ptr
 
 NEG_INF = float("-inf")
+# TMA-pipelined DepthwiseConv kernels (csrc/det_tma.cu) wherever the views are TMA-addressable; OCRS_DET_TMA=0 keeps the
+# synchronous tile kernels of det_fwd.cu / det_bwd.cu everywhere (A/B testing; they remain the path for W % 4 != 0).
+USE_TMA = os.environ.get("OCRS_DET_TMA", "1") == "1"
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -57,6 +62,8 @@ class _Sep:
     def __init__(self, mod):
         self.dw, self.pw, self.bn = mod.seq[0], mod.seq[1], mod.seq[2]
         self.cin, self.cout = self.pw.in_channels, self.pw.out_channels
+        # the block whose raw output IS this block's input and whose d_a this block's depthwise backward writes last
+        self.producer: _Sep | None = None
 
     def params(self):
         return [self.dw.weight, self.pw.weight, self.bn.weight, self.bn.bias]
@@ -68,11 +75,18 @@ class _Sep:
         if y is None:
             y = new_view(N, self.cout, H, W, dev)
         lib = _lib.lib()
-        rows = lib.ocrs_det_dwpw_partial_rows(N, H, W)
-        partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
-        call("ocrs_det_dwpw_fwd", inp.p, inp.ss, N, self.cin, H, W, *inp.xfp(), ptr(self.dw.weight),
-             ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st,
-             meta=4.0 * N * H * W * (self.cin + self.cout))
+        tma = USE_TMA and bool(lib.ocrs_det_tma_supported(inp.p, inp.ss, y.p, y.ss, H, W))
+        meta = 4.0 * N * H * W * (self.cin + self.cout)
+        if tma:  # TMA-pipelined persistent kernel (csrc/det_tma.cu)
+            rows = lib.ocrs_det_sep_fwd_rows(N, H, W, self.cout)
+            partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
+            call("ocrs_det_sep_fwd", inp.p, inp.ss, N, self.cin, H, W, *inp.xfp(), ptr(self.dw.weight),
+                 ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st, meta=meta)
+        else:
+            rows = lib.ocrs_det_dwpw_partial_rows(N, H, W)
+            partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
+            call("ocrs_det_dwpw_fwd", inp.p, inp.ss, N, self.cin, H, W, *inp.xfp(), ptr(self.dw.weight),
+                 ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st, meta=meta)
         if xf_dst is None:
             buf = torch.empty((3, self.cout), dtype=torch.float32, device=dev)
             xf_dst = (buf[0], buf[1], buf[2])
@@ -88,19 +102,26 @@ class _Sep:
             save[id(self)] = (inp, y, stats, bool(training))
         return y
 
-    def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False):
+    def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False, bn_pending=None):
         """d_a: gradient w.r.t. this block's activated output. Writes the gradient w.r.t. the
-        block's (activated) input into `dx`; returns [d_wdw, d_wpw, d_gamma, d_beta]."""
+        block's (activated) input into `dx`; returns [d_wdw, d_wpw, d_gamma, d_beta].
+        `bn_pending`: dict id(block) -> (partials, rows) of BatchNorm-backward sums already produced by the
+        kernel that wrote that block's d_a; this call consumes its own entry and, when its depthwise backward is
+        the final writer of the upstream block's d_a (`self.producer`), leaves that block's entry."""
         inp, y, stats, training = saved.pop(id(self))
         dev = y.t.device
         lib = _lib.lib()
         H, W, HW = y.H, y.W, y.H * y.W
         co, ci = self.cout, self.cin
-        rows = lib.ocrs_reduce_rows(N, HW)
-        part = torch.empty((rows, 2, co), dtype=torch.float32, device=dev)
         ysc, ysh, ylo = y.xfp()
-        call("ocrs_bnrelu_bwd_reduce", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, ysc, ysh, ylo, ptr(stats[0]),
-             ptr(stats[1]), ptr(part), st, meta=4.0 * N * HW * 2 * co)
+        mine = bn_pending.pop(id(self), None) if bn_pending is not None else None
+        if mine is not None:
+            part, rows = mine
+        else:
+            rows = lib.ocrs_reduce_rows(N, HW)
+            part = torch.empty((rows, 2, co), dtype=torch.float32, device=dev)
+            call("ocrs_bnrelu_bwd_reduce", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, ysc, ysh, ylo, ptr(stats[0]),
+                 ptr(stats[1]), ptr(part), st, meta=4.0 * N * HW * 2 * co)
         coef = torch.empty((5, co), dtype=torch.float32, device=dev)  # dgamma, dbeta, k1, k2, k3
         call("ocrs_bn_bwd_finalize", ptr(part), rows, co, float(N * HW), ptr(self.bn.weight), ptr(stats[0]),
              ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), int(training), st)
@@ -114,13 +135,28 @@ class _Sep:
              ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
         d_wpw = torch.empty_like(self.pw.weight)
         _finalize(wpart, workers, co * ci, d_wpw, st)
-        drows = lib.ocrs_det_dw_bwd_rows(N, H, W)
-        dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
         if dx is None:
             dx = new_view(N, ci, H, W, dev)
-        call("ocrs_det_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
-             dx.ss, int(accumulate), ptr(dpart), st, meta=4.0 * N * HW * 3 * ci)
         d_wdw = torch.empty_like(self.dw.weight)
+        if USE_TMA and lib.ocrs_det_tma_supported(g.p, g.ss, inp.p, inp.ss, H, W) and lib.ocrs_det_tma_supported(dx.p, dx.ss, dx.p, dx.ss, H, W):
+            drows = lib.ocrs_det_sep_dw_bwd_rows(N, H, W, ci)
+            dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
+            up = self.producer if (bn_pending is not None and self.producer is not None and id(self.producer) in saved) else None
+            if up is not None:
+                up_stats = saved[id(up)][2]
+                bnp = torch.empty((drows, 2, ci), dtype=torch.float32, device=dev)
+                call("ocrs_det_sep_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
+                     dx.ss, int(accumulate), ptr(dpart), ptr(up_stats[0]), ptr(up_stats[1]), ptr(bnp), st,
+                     meta=4.0 * N * HW * (3 + int(accumulate)) * ci)
+                bn_pending[id(up)] = (bnp, drows)
+            else:
+                call("ocrs_det_sep_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
+                     dx.ss, int(accumulate), ptr(dpart), None, None, None, st, meta=4.0 * N * HW * (3 + int(accumulate)) * ci)
+        else:
+            drows = lib.ocrs_det_dw_bwd_rows(N, H, W)
+            dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
+            call("ocrs_det_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
+                 dx.ss, int(accumulate), ptr(dpart), st, meta=4.0 * N * HW * 3 * ci)
         _finalize(dpart, drows, ci * 9, d_wdw, st)
         return [d_wdw, d_wpw, coef[0].clone(), coef[1].clone()], dx
 
@@ -138,6 +174,10 @@ class _Plan:
         self.contract = [[_Sep(m.contract.seq[0]), _Sep(m.contract.seq[1])] for m in model.up]
         self.out = model.out_conv[0]
         self.depth = d
+        self.in_conv[1].producer = self.in_conv[0]
+        self.down[0][0].producer = self.in_conv[1]  # skip connection: this (accumulating) backward runs after Up's
+        for pair in self.down + self.contract:
+            pair[1].producer = pair[0]
 
     def all_params(self):
         ps = []
@@ -239,6 +279,7 @@ class _DetFunction(torch.autograd.Function):
         dprob = dprob.contiguous().float()
         grads: dict = {}
         recs = ctx.recs
+        pend: dict = {}
 
         def put(tensors, gs):
             for t, g in zip(tensors, gs):
@@ -259,10 +300,10 @@ class _DetFunction(torch.autograd.Function):
             # up path, in reverse of forward order: up[0] first
             for i in range(L):
                 c = d[i]
-                gB, d_mid = plan.contract[i][1].backward(recs, d_a, N, st, None)
+                gB, d_mid = plan.contract[i][1].backward(recs, d_a, N, st, None, bn_pending=pend)
                 put(plan.contract[i][1].params(), gB)
                 dcat[i] = new_view(N, 2 * c, hs[i], ws[i], dev)
-                gA, _ = plan.contract[i][0].backward(recs, d_mid, N, st, dcat[i])
+                gA, _ = plan.contract[i][0].backward(recs, d_mid, N, st, dcat[i], bn_pending=pend)
                 put(plan.contract[i][0].params(), gA)
                 # ConvTranspose2d
                 t = plan.upT[i]
@@ -291,17 +332,17 @@ class _DetFunction(torch.autograd.Function):
                 d_full = new_view(N, b.C, b.H, b.W, dev)
                 call("ocrs_det_pool2_bwd", b.p, b.ss, N, b.C, b.H, b.W, *b.xfp(), d_pooled.p, d_pooled.ss,
                      d_full.p, d_full.ss, st)
-                gB, d_mid = plan.down[i][1].backward(recs, d_full, N, st, None)
+                gB, d_mid = plan.down[i][1].backward(recs, d_full, N, st, None, bn_pending=pend)
                 put(plan.down[i][1].params(), gB)
                 # input of down[i] is the skip half of cat[i]; its gradient already holds the Up-path part
                 dskip = dcat[i].chan(d[i], 2 * d[i])
-                gA, _ = plan.down[i][0].backward(recs, d_mid, N, st, dskip, accumulate=True)
+                gA, _ = plan.down[i][0].backward(recs, d_mid, N, st, dskip, accumulate=True, bn_pending=pend)
                 put(plan.down[i][0].params(), gA)
                 d_pooled = dskip
             # in_conv: d_pooled is now the gradient w.r.t. the activated in_conv output
-            gB, d_mid = plan.in_conv[1].backward(recs, d_pooled, N, st, None)
+            gB, d_mid = plan.in_conv[1].backward(recs, d_pooled, N, st, None, bn_pending=pend)
             put(plan.in_conv[1].params(), gB)
-            gA, dx = plan.in_conv[0].backward(recs, d_mid, N, st, None)
+            gA, dx = plan.in_conv[0].backward(recs, d_mid, N, st, None, bn_pending=pend)
             put(plan.in_conv[0].params(), gA)
         dxt = dx.t if ctx.needs_input_grad[1] else None
         out = [None, dxt] + [grads.get(id(p)) for p in plan.all_params()]

@@ -29,7 +29,11 @@ def _apply_xf(x, xf):
     return torch.maximum(x * sc[None, :, None, None] + sh[None, :, None, None], lo[None, :, None, None])
 
 
-@pytest.mark.parametrize("N,cin,cout,H,W,with_xf", [(2, 1, 8, 37, 45, False), (2, 8, 16, 64, 64, True), (1, 16, 16, 33, 70, True), (2, 64, 32, 9, 12, True), (1, 128, 256, 5, 3, True), (1, 24, 40, 17, 19, True)])
+@pytest.mark.parametrize("N,cin,cout,H,W,with_xf", [(2, 1, 8, 37, 45, False), (2, 8, 16, 64, 64, True), (1, 16, 16, 33, 70, True), (2, 64, 32, 9, 12, True), (1, 128, 256, 5, 3, True), (1, 24, 40, 17, 19, True),
+                                                         # TMA-addressable shapes (W % 4 == 0): csrc/det_tma.cu
+                                                         (2, 1, 8, 40, 36, False), (1, 16, 16, 68, 100, True), (2, 32, 16, 96, 64, True),
+                                                         (1, 64, 32, 32, 40, True), (1, 16, 32, 36, 44, True), (1, 256, 128, 8, 16, True),
+                                                         (3, 8, 8, 33, 132, True)])
 def test_separable_block_fwd_bwd(N, cin, cout, H, W, with_xf):
     from ocrs_models_b200.det_engine import View, _Sep, new_view
     from ocrs_models_b200.models import _separable
@@ -91,6 +95,45 @@ def test_dw_bwd_accumulate_into_strided_view():
     call("ocrs_det_dw_bwd", ptr(gr), C * H * W, ptr(gr), C * H * W, N, C, H, W, None, None, None, ptr(w),
          base.data_ptr() + 4 * dst_off, 2 * C * H * W, 1, None, _stream())
     assert rel_l2(base, ref) < 1e-6
+
+
+@pytest.mark.parametrize("N,C,H,W,acc", [(2, 8, 40, 36, True), (1, 5, 70, 132, False), (2, 16, 32, 64, True), (1, 1, 9, 8, False)])
+def test_tma_dw_bwd_with_fused_upstream_bn_reduction(N, C, H, W, acc):
+    """ocrs_det_sep_dw_bwd: dx (accumulated into a strided channel slice), dw weight gradient, and the BatchNorm-backward
+    sums of the block that produced x, vs the separate kernels (ocrs_det_dw_bwd + ocrs_bnrelu_bwd_reduce) and fp64."""
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200._lib import call, ptr
+
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(C * H)
+    gr = torch.randn(N, C, H, W, generator=g)
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(C, 1, 3, 3, generator=g)
+    xf = _rand_xf(C, g)
+    mean, invstd = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    base = torch.randn(N, 2 * C, H, W, generator=g)
+    xa = _apply_xf(x, xf).double()
+    wd = w.double().requires_grad_(True)
+    xa.requires_grad_(True)
+    out = F.conv2d(xa, wd, padding=1, groups=C)
+    out.backward(gr.double())
+    ref_dx = xa.grad + (base[:, C:].double() if acc else 0)
+    dz = ref_dx * (xa > 0)
+    yhat = (x.double() - mean[None, :, None, None]) * invstd[None, :, None, None]
+    ref_bn = torch.stack([dz.sum((0, 2, 3)), (dz * yhat).sum((0, 2, 3))])
+    grd, xd, wdv, based = gr.cuda(), x.cuda(), w.cuda(), base.cuda()
+    xfd = [t.cuda() for t in xf]
+    rows = lib.ocrs_det_sep_dw_bwd_rows(N, H, W, C)
+    wpart = torch.full((rows, C, 9), float("nan"), device="cuda")
+    bnpart = torch.full((rows, 2, C), float("nan"), device="cuda")
+    md, isd = mean.cuda(), invstd.cuda()
+    call("ocrs_det_sep_dw_bwd", ptr(grd), C * H * W, ptr(xd), C * H * W, N, C, H, W, *[ptr(t) for t in xfd], ptr(wdv),
+         based.data_ptr() + 4 * C * H * W, 2 * C * H * W, int(acc), ptr(wpart), ptr(md), ptr(isd), ptr(bnpart), _stream())
+    torch.cuda.synchronize()
+    assert rel_l2(based[:, C:], ref_dx) < 1e-6
+    assert torch.equal(based[:, :C].cpu(), base[:, :C])  # the other half of the concat gradient is untouched
+    assert rel_l2(wpart.double().sum(0).reshape(C, 1, 3, 3), wd.grad) < 1e-5
+    assert rel_l2(bnpart.double().sum(0), ref_bn) < 1e-5
 
 
 @pytest.mark.parametrize("H,W", [(64, 64), (37, 51), (2, 3)])
