@@ -50,10 +50,13 @@ SIGNATURES: dict[str, list] = {
     "ocrs_plane_sum": [P, L, I, I, L, P, P],
     # TMA-pipelined DepthwiseConv kernels (csrc/det_tma.cu)
     "ocrs_det_tma_supported": [P, L, P, L, I, I],
+    "ocrs_det_sep_channels_ok": [I, I],
     "ocrs_det_sep_fwd_rows": [I, I, I, I],
     "ocrs_det_sep_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, P, P],
     "ocrs_det_sep_dw_bwd_rows": [I, I, I, I],
     "ocrs_det_sep_dw_bwd": [P, L, P, L, I, I, I, I, P, P, P, P, P, L, I, P, P, P, P, P],
+    "ocrs_det_sep_pw_wgrad_workers": [I, I, I, I, I],
+    "ocrs_det_sep_pw_wgrad": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, L, I, P, P, P, P, P, P],
     # GEMM / im2col (csrc/gemm.cu)
     "ocrs_gemm_stat_rows": [I],
     "ocrs_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],

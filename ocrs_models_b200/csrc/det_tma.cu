@@ -32,6 +32,7 @@ constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 256;
 // shared-memory floats of a box of `ch` planes, padded so that the next TMA destination stays 128-byte aligned
 constexpr int box_floats(int ch) { return (ch * PLANE + 31) / 32 * 32; }
+constexpr int box_floats2(int floats) { return (floats + 31) / 32 * 32; }
 
 // Sum over the 32 lanes of v[j] for all j at once; lane l returns the total of column (l % NV).
 template <int NV>
@@ -94,6 +95,45 @@ __device__ __forceinline__ bool tile_masks(int x0, int y0, int H, int W, int lan
 #pragma unroll
   for (int q = 0; q < 3; ++q) { const int gx = x0 - 1 + lane + q; colok[q] = gx >= 0 && gx < W; }
   return border;
+}
+
+// One stage (FCH channels) of the forward block: depthwise 3x3 on the activated window, then the 1x1 contraction.
+template <bool XF, bool BORDER, int CO_T, int FCH>
+__device__ __forceinline__ void fwd_chunk(const float* st, const float* sdw, const float* spw, const float* sxf, int Cin,
+                                          int c0, const bool (&rowok)[PPT + 2], const bool (&colok)[3],
+                                          float (&acc)[PPT][CO_T]) {
+#pragma unroll
+  for (int c = 0; c < FCH; ++c) {
+    float v[PPT + 2][3];
+    const int ci = c0 + c;
+    float sc = 1.f, sh = 0.f, lo = 0.f;
+    if (XF) { sc = sxf[ci]; sh = sxf[Cin + ci]; lo = sxf[2 * Cin + ci]; }
+    load_window<XF, BORDER>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
+    const float4 w0 = *reinterpret_cast<const float4*>(sdw + ci * 12);
+    const float4 w1 = *reinterpret_cast<const float4*>(sdw + ci * 12 + 4);
+    const float w8 = sdw[ci * 12 + 8];
+    float d[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      float t = v[i][0] * w0.x;
+      t = fmaf(v[i][1], w0.y, t); t = fmaf(v[i][2], w0.z, t);
+      t = fmaf(v[i + 1][0], w0.w, t); t = fmaf(v[i + 1][1], w1.x, t); t = fmaf(v[i + 1][2], w1.y, t);
+      t = fmaf(v[i + 2][0], w1.z, t); t = fmaf(v[i + 2][1], w1.w, t); t = fmaf(v[i + 2][2], w8, t);
+      d[i] = t;
+    }
+    const float4* w4 = reinterpret_cast<const float4*>(spw + ci * CO_T);
+#pragma unroll
+    for (int o4 = 0; o4 < CO_T / 4; ++o4) {
+      const float4 wv = w4[o4];
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        acc[i][o4 * 4 + 0] = fmaf(d[i], wv.x, acc[i][o4 * 4 + 0]);
+        acc[i][o4 * 4 + 1] = fmaf(d[i], wv.y, acc[i][o4 * 4 + 1]);
+        acc[i][o4 * 4 + 2] = fmaf(d[i], wv.z, acc[i][o4 * 4 + 2]);
+        acc[i][o4 * 4 + 3] = fmaf(d[i], wv.w, acc[i][o4 * 4 + 3]);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -173,40 +213,10 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
     const int s = j % NSTAGE;
     tma::mbar_wait(tma::smem_u32(&bars[s]), (j / NSTAGE) & 1);
     const float* st = stages + s * STAGE_FLOATS + (PPT * warp) * BW + lane + 3;
-    const int c0 = ch * FCH;
-    const int nc = min(FCH, Cin - c0);
-    for (int c = 0; c < nc; ++c) {
-      float v[PPT + 2][3];
-      const int ci = c0 + c;
-      const float sc = has_xf ? sxf[ci] : 1.f, sh = has_xf ? sxf[Cin + ci] : 0.f, lo = has_xf ? sxf[2 * Cin + ci] : 0.f;
-      if (!has_xf) load_window<false, false>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
-      else if (border) load_window<true, true>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
-      else load_window<true, false>(st + c * PLANE, sc, sh, lo, rowok, colok, v);
-      const float4 w0 = *reinterpret_cast<const float4*>(sdw + ci * 12);
-      const float4 w1 = *reinterpret_cast<const float4*>(sdw + ci * 12 + 4);
-      const float w8 = sdw[ci * 12 + 8];
-      float d[PPT];
-#pragma unroll
-      for (int i = 0; i < PPT; ++i) {
-        float t = v[i][0] * w0.x;
-        t = fmaf(v[i][1], w0.y, t); t = fmaf(v[i][2], w0.z, t);
-        t = fmaf(v[i + 1][0], w0.w, t); t = fmaf(v[i + 1][1], w1.x, t); t = fmaf(v[i + 1][2], w1.y, t);
-        t = fmaf(v[i + 2][0], w1.z, t); t = fmaf(v[i + 2][1], w1.w, t); t = fmaf(v[i + 2][2], w8, t);
-        d[i] = t;
-      }
-      const float4* w4 = reinterpret_cast<const float4*>(spw + ci * CO_T);
-#pragma unroll
-      for (int o4 = 0; o4 < CO_T / 4; ++o4) {
-        const float4 wv = w4[o4];
-#pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-          acc[i][o4 * 4 + 0] = fmaf(d[i], wv.x, acc[i][o4 * 4 + 0]);
-          acc[i][o4 * 4 + 1] = fmaf(d[i], wv.y, acc[i][o4 * 4 + 1]);
-          acc[i][o4 * 4 + 2] = fmaf(d[i], wv.z, acc[i][o4 * 4 + 2]);
-          acc[i][o4 * 4 + 3] = fmaf(d[i], wv.w, acc[i][o4 * 4 + 3]);
-        }
-      }
-    }
+    const int c0 = ch * FCH;  // Cin is 1 (FCH = 1) or a multiple of FCH (checked on the host)
+    if (!has_xf) fwd_chunk<false, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc);
+    else if (border) fwd_chunk<true, true, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc);
+    else fwd_chunk<true, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc);
     __syncthreads();  // every thread is done with stage s
     if (tid == 0 && j + NSTAGE < total) issue(j + NSTAGE);
     if (++ch == nchunks) {
@@ -214,20 +224,36 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
       ++k;
       const int gx = x0 + lane, gy0 = y0 + PPT * warp;
       float sv[2 * CO_T];
+      float* yp = a.y + (size_t)n * a.y_ss + ((size_t)co0 * a.H + gy0) * a.W + gx;  // Cout % CO_T == 0 (host check)
+      const size_t HW = (size_t)a.H * a.W;
+      if (x0 + TW <= a.W && y0 + TH <= a.H) {  // full tile (uniform per CTA): no bounds checks
 #pragma unroll
-      for (int o = 0; o < CO_T; ++o) {
-        float s1 = 0.f, s2 = 0.f;
-        float* yp = a.y + (size_t)n * a.y_ss + ((size_t)(co0 + o) * a.H + gy0) * a.W + gx;
+        for (int o = 0; o < CO_T; ++o) {
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-          if (gx < a.W && gy0 + i < a.H) {
+          for (int i = 0; i < PPT; ++i) {
             s1 += acc[i][o];
             s2 = fmaf(acc[i][o], acc[i][o], s2);
-            if (co0 + o < a.Cout) yp[(size_t)i * a.W] = acc[i][o];
+            yp[o * HW + (size_t)i * a.W] = acc[i][o];
           }
+          sv[o] = s1;
+          sv[CO_T + o] = s2;
         }
-        sv[o] = s1;
-        sv[CO_T + o] = s2;
+      } else {
+#pragma unroll
+        for (int o = 0; o < CO_T; ++o) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < PPT; ++i) {
+            if (gx < a.W && gy0 + i < a.H) {
+              s1 += acc[i][o];
+              s2 = fmaf(acc[i][o], acc[i][o], s2);
+              yp[o * HW + (size_t)i * a.W] = acc[i][o];
+            }
+          }
+          sv[o] = s1;
+          sv[CO_T + o] = s2;
+        }
       }
       if (a.partials) stat += warp_colsum<2 * CO_T>(sv, lane);
     }
@@ -418,6 +444,219 @@ int dw_ctas_per_chunk(int N, int H, int W, int C) {
   return (int)(sp < per ? sp : per);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pointwise (1x1) weight gradient dWpw[co][ci] = sum_p dy[co][p] * dwout[ci][p] (dy = BatchNorm/ReLU backward of d_a
+// rebuilt on the fly, dwout = dw3x3(xform(x)) recomputed). Same warp-level mma.sync m16n8k8 3xTF32 contraction
+// as pw_wgrad_mma_kernel (det_bwd.cu): M = 16 output channels, N = 16 input channels, K = pixels, operands built in
+// fragment layout in registers. What changed is everything around it:
+//   * the haloed x tile (16 channels x 10 rows x 40 columns) arrives by TMA into a 2-stage ring while the previous
+//     tile is computed, and is activated ONCE per element by a vectorised pass into a work buffer whose plane
+//     stride (404 floats) makes the fragment reads bank-conflict free (the old kernel activated every element up
+//     to nine times while gathering the stencil);
+//   * the d_a / y operands of a tile are loaded into registers before waiting for the tile (independent loads);
+//   * persistent CTAs, two per SM, no spills.
+constexpr int WTW = 32, WTH = 8;                  // tile: one row of 32 pixels per warp (4 k-steps of 8 pixels)
+constexpr int WBH = WTH + 2;                      // box rows
+constexpr int WPLANE = BW * WBH;                  // 400 floats per channel plane as landed by TMA
+constexpr int XS_PLANE = WPLANE + 4;              // activated copy: 404 = 20 (mod 32) -> fragment reads conflict free
+constexpr int WCH = 16;
+
+struct PwWgArgs {
+  const float *d_a, *y;
+  long long da_ss, y_ss;
+  const float *sc, *sh, *lo, *k1, *k2, *k3;       // dy = k1 * dz + k2 * y + k3, dz = d_a * [y * sc + sh > lo]
+  const float *isc, *ish, *ilo, *wdw;
+  float* partials;                                // [gridDim.x][Cout][Cin]
+  int Cout, Cin, H, W, N, tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void tf32_split2(float v, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+sep_pw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, PwWgArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE_FLOATS = box_floats2(WCH * WPLANE);
+  float* stages = reinterpret_cast<float*>(smem_raw);                   // [2][WCH * WPLANE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + 2 * STAGE_FLOATS);
+  float* xs = stages + 2 * STAGE_FLOATS + 16;                           // [WCH][XS_PLANE]
+  float* sred = xs + WCH * XS_PLANE;                                    // [8][256]
+  float* sxf = sred + 8 * 256;                                          // [3][16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cit = (a.Cin + 15) / 16;
+  const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
+  const int nco = min(16, a.Cout - co0), nci = min(16, a.Cin - ci0);
+  const size_t HW = (size_t)a.H * a.W;
+  if (tid < 16) {
+    const bool v = tid < nci && a.isc != nullptr;
+    sxf[tid] = v ? a.isc[ci0 + tid] : 1.f;
+    sxf[16 + tid] = v ? a.ish[ci0 + tid] : 0.f;
+    sxf[32 + tid] = v ? a.ilo[ci0 + tid] : -INFINITY;
+  }
+  // per-lane constants: its two output channels (g, g+8) and its two input channels (g, g+8)
+  float ksc[2], ksh[2], klo[2], kk1[2], kk2[2], kk3[2], wd[2][9];
+  bool cov[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int o = g + 8 * h;
+    cov[h] = o < nco;
+    const bool civ = o < nci;
+    ksc[h] = cov[h] ? a.sc[co0 + o] : 0.f; ksh[h] = cov[h] ? a.sh[co0 + o] : 0.f; klo[h] = cov[h] ? a.lo[co0 + o] : 0.f;
+    kk1[h] = cov[h] ? a.k1[co0 + o] : 0.f; kk2[h] = cov[h] ? a.k2[co0 + o] : 0.f; kk3[h] = cov[h] ? a.k3[co0 + o] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wd[h][q] = civ ? a.wdw[(size_t)(ci0 + o) * 9 + q] : 0.f;
+  }
+  if (tid == 0) {
+    tma::mbar_init(tma::smem_u32(&bars[0]), 1);
+    tma::mbar_init(tma::smem_u32(&bars[1]), 1);
+    tma::fence_barrier_init();
+    tma::prefetch_map(&xmap);
+  }
+  __syncthreads();
+  const int tiles = a.tiles_x * a.tiles_y;
+  const int total_tiles = a.N * tiles;
+  const int mine = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto decode = [&](int j, int& n, int& x0, int& y0) {
+    const int work = blockIdx.x + j * gridDim.x;
+    n = work / tiles;
+    const int r = work - n * tiles;
+    y0 = (r / a.tiles_x) * WTH;
+    x0 = (r % a.tiles_x) * WTW;
+  };
+  auto issue = [&](int j) {
+    int n, x0, y0;
+    decode(j, n, x0, y0);
+    const uint32_t bar = tma::smem_u32(&bars[j & 1]);
+    tma::mbar_expect_tx(bar, WCH * WPLANE * 4);
+    tma::load_4d(tma::smem_u32(stages + (j & 1) * STAGE_FLOATS), &xmap, x0 - 4, y0 - 1, ci0, n, bar);
+  };
+  if (tid == 0) {
+    if (mine > 0) issue(0);
+    if (mine > 1) issue(1);
+  }
+  float ctot[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ctot[j][q] = 0.f;
+
+  for (int j = 0; j < mine; ++j) {
+    int n, x0, y0;
+    decode(j, n, x0, y0);
+    // A operands of the whole tile row (4 k-steps x {t, t+4} x {g, g+8}): independent loads, issued before the wait
+    const int gy = y0 + warp;
+    float dav[4][4], yvv[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int h = q & 1, px = x0 + ks * 8 + t + 4 * (q >> 1);
+        dav[ks][q] = 0.f;
+        yvv[ks][q] = 0.f;
+        if (cov[h] && gy < a.H && px < a.W) {
+          const size_t off = (size_t)(co0 + g + 8 * h) * HW + (size_t)gy * a.W + px;
+          dav[ks][q] = a.d_a[(size_t)n * a.da_ss + off];
+          yvv[ks][q] = a.y[(size_t)n * a.y_ss + off];
+        }
+      }
+    tma::mbar_wait(tma::smem_u32(&bars[j & 1]), (j >> 1) & 1);
+    // activate the landed tile once, 4 elements at a time, into the conflict-free work buffer
+    {
+      const float* st = stages + (j & 1) * STAGE_FLOATS;
+      constexpr int V4_PER_PLANE = WPLANE / 4, V4_PER_ROW = BW / 4;
+      const int nplanes = (nci + 7) & ~7;  // planes the fragment reads touch; those past nci are zeroed
+      for (int e = tid; e < nplanes * V4_PER_PLANE; e += NTHREADS) {
+        const int c = e / V4_PER_PLANE, p4 = e - c * V4_PER_PLANE;
+        const int r = p4 / V4_PER_ROW, col = (p4 - r * V4_PER_ROW) * 4;
+        const int yy = y0 - 1 + r, xx = x0 - 4 + col;
+        float4 v = *reinterpret_cast<const float4*>(st + c * WPLANE + p4 * 4);
+        const float s = sxf[c], sh_ = sxf[16 + c], l = sxf[32 + c];
+        const bool rok = yy >= 0 && yy < a.H && c < nci;
+        v.x = (rok && xx >= 0 && xx < a.W) ? xform_apply(v.x, s, sh_, l) : 0.f;
+        v.y = (rok && xx + 1 >= 0 && xx + 1 < a.W) ? xform_apply(v.y, s, sh_, l) : 0.f;
+        v.z = (rok && xx + 2 >= 0 && xx + 2 < a.W) ? xform_apply(v.z, s, sh_, l) : 0.f;
+        v.w = (rok && xx + 3 >= 0 && xx + 3 < a.W) ? xform_apply(v.w, s, sh_, l) : 0.f;
+        *reinterpret_cast<float4*>(xs + c * XS_PLANE + p4 * 4) = v;
+      }
+    }
+    __syncthreads();  // xs complete, stage (j & 1) free
+    if (tid == 0 && j + 2 < mine) issue(j + 2);
+    float c[2][4];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[jj][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int h = q & 1;
+        const float yv = yvv[ks][q];
+        const float dz = (fmaf(yv, ksc[h], ksh[h]) > klo[h]) ? dav[ks][q] : 0.f;
+        const float dy = fmaf(kk1[h], dz, fmaf(kk2[h], yv, kk3[h]));
+        tf32_split2(cov[h] && gy < a.H && x0 + ks * 8 + t + 4 * (q >> 1) < a.W ? dy : 0.f, ah[q], al[q]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        if (8 * jj >= nci) continue;  // uniform: no input channels in this n-tile
+        // dwout[ci = 8jj + g][pixel t / t+4]: depthwise stencil on the activated tile
+        float b[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float* tp = xs + (8 * jj + g) * XS_PLANE + warp * BW + ks * 8 + t + 4 * e + 3;
+          float sacc = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) sacc = fmaf(tp[ky * BW + kx], wd[jj][ky * 3 + kx], sacc);
+          b[e] = sacc;
+        }
+        uint32_t bh0, bl0, bh1, bl1;
+        tf32_split2(b[0], bh0, bl0);
+        tf32_split2(b[1], bh1, bl1);
+        mma_tf32_16n8k8(c[jj], al, bh0, bh1);
+        mma_tf32_16n8k8(c[jj], ah, bl0, bl1);
+        mma_tf32_16n8k8(c[jj], ah, bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ctot[jj][q] += c[jj][q];  // flush: the tensor core's own accumulation stays short
+    __syncthreads();  // everyone is done with xs before the next tile overwrites it
+  }
+  // C fragment -> (co, ci): c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1); n-tile jj adds 8 to ci
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    sred[warp * 256 + g * 16 + 8 * jj + 2 * t] = ctot[jj][0];
+    sred[warp * 256 + g * 16 + 8 * jj + 2 * t + 1] = ctot[jj][1];
+    sred[warp * 256 + (g + 8) * 16 + 8 * jj + 2 * t] = ctot[jj][2];
+    sred[warp * 256 + (g + 8) * 16 + 8 * jj + 2 * t + 1] = ctot[jj][3];
+  }
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += sred[w * 256 + tid];
+  const int o = tid >> 4, ci = tid & 15;
+  if (o < nco && ci < nci) a.partials[((size_t)blockIdx.x * a.Cout + co0 + o) * a.Cin + ci0 + ci] = sum;
+}
+
+int pw_wgrad_workers(int N, int H, int W, int pairs) {
+  const long long tiles = (long long)N * ocrs_cdiv(W, WTW) * ocrs_cdiv(H, WTH);
+  long long per = (2 * OCRS_NUM_SMS + pairs - 1) / pairs;
+  if (per < 1) per = 1;
+  return (int)(tiles < per ? tiles : per);
+}
 }  // namespace
 
 extern "C" {
@@ -425,6 +664,12 @@ extern "C" {
 // 1 when the TMA-pipelined DepthwiseConv kernels can run on these views (16-byte aligned planes, W % 4 == 0).
 int ocrs_det_tma_supported(const float* x, long long x_ss, const float* y, long long y_ss, int H, int W) {
   return ocrs_plane_tma_ok(x, x_ss, H, W) && ocrs_plane_tma_ok(y, y_ss, H, W) && H >= 8 && W >= 8;
+}
+
+// 1 when ocrs_det_sep_fwd handles these channel counts (Cout a multiple of its 8/16-channel tile, Cin < 4 or a multiple of 4).
+int ocrs_det_sep_channels_ok(int Cin, int Cout) {
+  const int cot = Cout <= 8 ? 8 : 16;
+  return Cout % cot == 0 && (Cin < 4 || Cin % 4 == 0);
 }
 
 // Rows of the [rows][2][Cout] statistics partials ocrs_det_sep_fwd writes.
@@ -440,6 +685,7 @@ int ocrs_det_sep_fwd(const float* x, long long x_ss, int N, int Cin, int H, int 
   OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "sep_fwd: bad dims");
   OCRS_CHECK_ARG(ocrs_det_tma_supported(x, x_ss, y, y_ss, H, W), "sep_fwd: views are not TMA-addressable");
   const int cot = Cout <= 8 ? 8 : 16;
+  OCRS_CHECK_ARG(Cout % cot == 0 && (Cin < 4 || Cin % 4 == 0), "sep_fwd: channel counts %d -> %d unsupported (ocrs_det_sep_channels_ok)", Cin, Cout);
   FwdArgs a;
   a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.N = N; a.n_cot = ocrs_cdiv(Cout, cot);
   a.in_scale = in_scale; a.in_shift = in_shift; a.in_lo = in_lo; a.wdw = wdw; a.wpw = wpw;
@@ -506,6 +752,36 @@ int ocrs_det_sep_dw_bwd(const float* g, long long g_ss, const float* x, long lon
   const int ctas = a.ctas_per_chunk * ocrs_cdiv(C, DCH);
   sep_dw_bwd_tma_kernel<<<ctas, NTHREADS, smem, (cudaStream_t)stream>>>(gmap, xmap, a);
   OCRS_CHECK_LAUNCH("sep_dw_bwd_tma_kernel");
+  return 0;
+}
+
+// Rows ("workers") of the [workers][Cout][Cin] partials of ocrs_det_sep_pw_wgrad.
+int ocrs_det_sep_pw_wgrad_workers(int N, int H, int W, int Cout, int Cin) {
+  return pw_wgrad_workers(N, H, W, ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
+}
+
+// 1x1-convolution weight gradient of a DepthwiseConv block, TMA-staged; same contract as ocrs_det_pw_wgrad
+// (partials fully written; reduce with ocrs_finalize_partials).
+int ocrs_det_sep_pw_wgrad(const float* d_a, long long da_ss, const float* y, long long y_ss, int N, int Cout, int H,
+                          int W, const float* sc, const float* sh, const float* lo, const float* k1, const float* k2,
+                          const float* k3, const float* x, long long x_ss, int Cin, const float* isc, const float* ish,
+                          const float* ilo, const float* wdw, float* partials, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "sep_pw_wgrad: bad dims");
+  OCRS_CHECK_ARG(ocrs_plane_tma_ok(x, x_ss, H, W), "sep_pw_wgrad: x is not TMA-addressable");
+  PwWgArgs a;
+  a.d_a = d_a; a.y = y; a.da_ss = da_ss; a.y_ss = y_ss;
+  a.sc = sc; a.sh = sh; a.lo = lo; a.k1 = k1; a.k2 = k2; a.k3 = k3;
+  a.isc = isc; a.ish = ish; a.ilo = ilo; a.wdw = wdw; a.partials = partials;
+  a.Cout = Cout; a.Cin = Cin; a.H = H; a.W = W; a.N = N;
+  a.tiles_x = ocrs_cdiv(W, WTW); a.tiles_y = ocrs_cdiv(H, WTH);
+  CUtensorMap xmap;
+  if (ocrs_plane_map(&xmap, x, x_ss, N, Cin, H, W, BW, WBH, WCH)) return -1;
+  const int pairs = ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16);
+  const size_t smem = (size_t)2 * box_floats2(WCH * WPLANE) * 4 + 64 + (size_t)WCH * XS_PLANE * 4 + 8 * 256 * 4 + 48 * 4 + 128;
+  OCRS_CUDA(cudaFuncSetAttribute(sep_pw_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(pw_wgrad_workers(N, H, W, pairs), pairs);
+  sep_pw_wgrad_tma_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(xmap, a);
+  OCRS_CHECK_LAUNCH("sep_pw_wgrad_tma_kernel");
   return 0;
 }
 

@@ -75,7 +75,8 @@ class _Sep:
         if y is None:
             y = new_view(N, self.cout, H, W, dev)
         lib = _lib.lib()
-        tma = USE_TMA and bool(lib.ocrs_det_tma_supported(inp.p, inp.ss, y.p, y.ss, H, W))
+        tma = (USE_TMA and bool(lib.ocrs_det_tma_supported(inp.p, inp.ss, y.p, y.ss, H, W))
+               and bool(lib.ocrs_det_sep_channels_ok(self.cin, self.cout)))
         meta = 4.0 * N * H * W * (self.cin + self.cout)
         if tma:  # TMA-pipelined persistent kernel (csrc/det_tma.cu)
             rows = lib.ocrs_det_sep_fwd_rows(N, H, W, self.cout)
@@ -129,10 +130,16 @@ class _Sep:
         g = new_view(N, ci, H, W, dev)
         call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
              meta=4.0 * N * HW * (2 * co + ci))
-        workers = lib.ocrs_det_pw_wgrad_workers(N, H, W)
-        wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
-        call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
-             ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
+        if USE_TMA and lib.ocrs_det_tma_supported(inp.p, inp.ss, inp.p, inp.ss, H, W):
+            workers = lib.ocrs_det_sep_pw_wgrad_workers(N, H, W, co, ci)
+            wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+            call("ocrs_det_sep_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
+                 ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
+        else:
+            workers = lib.ocrs_det_pw_wgrad_workers(N, H, W)
+            wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+            call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
+                 ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
         d_wpw = torch.empty_like(self.pw.weight)
         _finalize(wpart, workers, co * ci, d_wpw, st)
         if dx is None:

@@ -97,6 +97,35 @@ def test_dw_bwd_accumulate_into_strided_view():
     assert rel_l2(base, ref) < 1e-6
 
 
+@pytest.mark.parametrize("N,cin,cout,H,W", [(2, 8, 16, 40, 36), (1, 1, 8, 17, 64), (2, 32, 16, 20, 72), (1, 16, 40, 9, 132), (1, 24, 8, 33, 32)])
+def test_tma_pw_wgrad_matches_fp64(N, cin, cout, H, W):
+    """ocrs_det_sep_pw_wgrad (TMA-staged tiles, mma.sync 3xTF32) vs an fp64 einsum of dy and the depthwise output."""
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200._lib import call, ptr
+
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(N, cin, H, W, generator=g)
+    y = torch.randn(N, cout, H, W, generator=g)
+    d_a = torch.randn(N, cout, H, W, generator=g)
+    wdw = torch.randn(cin, 1, 3, 3, generator=g)
+    xf, yxf = _rand_xf(cin, g), _rand_xf(cout, g)
+    k1, k2, k3 = (torch.randn(cout, generator=g) for _ in range(3))
+    xa = _apply_xf(x, xf).double()
+    dwout = F.conv2d(xa, wdw.double(), padding=1, groups=cin)
+    act = (y.double() * yxf[0][None, :, None, None] + yxf[1][None, :, None, None]) > 0
+    dy = k1[None, :, None, None] * (d_a.double() * act) + k2[None, :, None, None] * y.double() + k3[None, :, None, None]
+    ref = torch.einsum("nohw,nihw->oi", dy, dwout)
+    workers = lib.ocrs_det_sep_pw_wgrad_workers(N, H, W, cout, cin)
+    part = torch.full((workers, cout, cin), float("nan"), device="cuda")
+    dev = [t.cuda() for t in (d_a, y, *yxf, k1, k2, k3, x, *xf, wdw)]
+    call("ocrs_det_sep_pw_wgrad", ptr(dev[0]), cout * H * W, ptr(dev[1]), cout * H * W, N, cout, H, W, ptr(dev[2]), ptr(dev[3]),
+         ptr(dev[4]), ptr(dev[5]), ptr(dev[6]), ptr(dev[7]), ptr(dev[8]), cin * H * W, cin, ptr(dev[9]), ptr(dev[10]), ptr(dev[11]),
+         ptr(dev[12]), ptr(part), _stream())
+    torch.cuda.synchronize()
+    assert rel_l2(part.double().sum(0), ref) < 2e-5
+
+
 @pytest.mark.parametrize("N,C,H,W,acc", [(2, 8, 40, 36, True), (1, 5, 70, 132, False), (2, 16, 32, 64, True), (1, 1, 9, 8, False)])
 def test_tma_dw_bwd_with_fused_upstream_bn_reduction(N, C, H, W, acc):
     """ocrs_det_sep_dw_bwd: dx (accumulated into a strided channel slice), dw weight gradient, and the BatchNorm-backward
