@@ -101,7 +101,7 @@ __device__ __forceinline__ bool tile_masks(int x0, int y0, int H, int W, int lan
 template <bool XF, bool BORDER, int CO_T, int FCH>
 __device__ __forceinline__ void fwd_chunk(const float* st, const float* sdw, const float* spw, const float* sxf, int Cin,
                                           int c0, const bool (&rowok)[PPT + 2], const bool (&colok)[3],
-                                          float (&acc)[PPT][CO_T]) {
+                                          float (&acc)[PPT][CO_T], float* dwo, size_t plane, int W, unsigned okmask) {
 #pragma unroll
   for (int c = 0; c < FCH; ++c) {
     float v[PPT + 2][3];
@@ -120,6 +120,11 @@ __device__ __forceinline__ void fwd_chunk(const float* st, const float* sdw, con
       t = fmaf(v[i + 1][0], w0.w, t); t = fmaf(v[i + 1][1], w1.x, t); t = fmaf(v[i + 1][2], w1.y, t);
       t = fmaf(v[i + 2][0], w1.z, t); t = fmaf(v[i + 2][1], w1.w, t); t = fmaf(v[i + 2][2], w8, t);
       d[i] = t;
+    }
+    if (dwo) {  // uniform: training-mode forward of co-tile 0 keeps the depthwise output for the weight gradient
+#pragma unroll
+      for (int i = 0; i < PPT; ++i)
+        if (okmask & (1u << i)) dwo[(size_t)ci * plane + (size_t)i * W] = d[i];
     }
     const float4* w4 = reinterpret_cast<const float4*>(spw + ci * CO_T);
 #pragma unroll
@@ -142,6 +147,7 @@ struct FwdArgs {
   int Cin, Cout, H, W, N, n_cot;
   const float *in_scale, *in_shift, *in_lo, *wdw, *wpw;
   float* y; long long y_ss;
+  float* dwo;       // [N][Cin][H][W] depthwise output saved for the 1x1 weight gradient, or null
   float* partials;  // [gridDim.x / n_cot][2][Cout] or null
   TileWalk walk;    // sp0 / sp_stride filled per CTA
 };
@@ -201,6 +207,9 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
   bool border = false;
   int n = 0, x0 = 0, y0 = 0;
   int k = 0, ch = 0;
+  const size_t plane = (size_t)a.H * a.W;
+  float* dwo_t = nullptr;   // this thread's first pixel of the saved depthwise output (channel 0), current tile
+  unsigned okmask = 0;      // which of its PPT pixels are inside the image
   for (int j = 0; j < total; ++j) {
     if (ch == 0) {
       walk.decode(k, n, x0, y0);
@@ -209,14 +218,21 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
 #pragma unroll
         for (int o = 0; o < CO_T; ++o) acc[i][o] = 0.f;
       border = tile_masks(x0, y0, a.H, a.W, lane, warp, rowok, colok);
+      if (a.dwo != nullptr && cot == 0) {
+        const int gx = x0 + lane, gy0 = y0 + PPT * warp;
+        dwo_t = a.dwo + ((size_t)n * Cin * a.H + gy0) * a.W + gx;
+        okmask = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) okmask |= (gx < a.W && gy0 + i < a.H) ? (1u << i) : 0u;
+      }
     }
     const int s = j % NSTAGE;
     tma::mbar_wait(tma::smem_u32(&bars[s]), (j / NSTAGE) & 1);
     const float* st = stages + s * STAGE_FLOATS + (PPT * warp) * BW + lane + 3;
     const int c0 = ch * FCH;  // Cin is 1 (FCH = 1) or a multiple of FCH (checked on the host)
-    if (!has_xf) fwd_chunk<false, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc);
-    else if (border) fwd_chunk<true, true, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc);
-    else fwd_chunk<true, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc);
+    if (!has_xf) fwd_chunk<false, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc, dwo_t, plane, a.W, okmask);
+    else if (border) fwd_chunk<true, true, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc, dwo_t, plane, a.W, okmask);
+    else fwd_chunk<true, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc, dwo_t, plane, a.W, okmask);
     __syncthreads();  // every thread is done with stage s
     if (tid == 0 && j + NSTAGE < total) issue(j + NSTAGE);
     if (++ch == nchunks) {
@@ -657,6 +673,140 @@ int pw_wgrad_workers(int N, int H, int W, int pairs) {
   if (per < 1) per = 1;
   return (int)(tiles < per ? tiles : per);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1x1 weight gradient from the SAVED depthwise output: dWpw[co][ci] = sum_p dy[co][p] * dwo[ci][p]. The detection
+// step on B200 is bound by instruction issue, not by HBM (ncu: 50-68 % issue-active at 25-40 % DRAM throughput), so
+// the forward stores the depthwise output (4*Cin bytes / pixel) and this kernel streams both operands straight from
+// global memory in mma.sync fragment layout: no halo, no stencil recompute, no shared memory until the final
+// reduction. ~10 warp instructions per pixel instead of ~36 for the recomputing kernel above.
+struct PwWg2Args {
+  const float *d_a, *y, *dwo;
+  long long da_ss, y_ss;
+  const float *sc, *sh, *lo, *k1, *k2, *k3;
+  float* partials;  // [gridDim.x][Cout][Cin]
+  int Cout, Cin, N;
+  long long HW;
+};
+// Operands are staged by cp.async.cg (16 bytes = 4 pixels of one channel plane per request: every warp request
+// covers 512 contiguous bytes of ONE plane, where gathering straight in fragment layout touched 8 planes per
+// request and ran into the L1 tag rate) into a 4-stage ring of [48 planes][128 pixels] whose plane stride (132)
+// makes the fragment reads (8 planes x 4 pixels per warp request) bank-conflict free.
+constexpr int GPX = 128;           // pixels per stage
+constexpr int GPS = GPX + 4;       // plane stride in shared memory
+constexpr int GSTAGES = 4;
+constexpr int GPLANES = 48;        // d_a[16] | y[16] | dwo[16]
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+pw_wgrad_saved_kernel(PwWg2Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);  // [GSTAGES][GPLANES][GPS]; reused for the final reduction
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cit = (a.Cin + 15) / 16;
+  const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
+  const int nco = min(16, a.Cout - co0), nci = min(16, a.Cin - ci0);
+  float ksc[2], ksh[2], klo[2], kk1[2], kk2[2], kk3[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int o = g + 8 * h;
+    const bool cov = o < nco;
+    ksc[h] = cov ? a.sc[co0 + o] : 0.f; ksh[h] = cov ? a.sh[co0 + o] : 0.f; klo[h] = cov ? a.lo[co0 + o] : 0.f;
+    kk1[h] = cov ? a.k1[co0 + o] : 0.f; kk2[h] = cov ? a.k2[co0 + o] : 0.f; kk3[h] = cov ? a.k3[co0 + o] : 0.f;
+  }
+  float ctot[2][4], c[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ctot[j][q] = 0.f; c[j][q] = 0.f; }
+  const long long chunks_per_n = (a.HW + GPX - 1) / GPX;
+  const long long total = chunks_per_n * a.N;
+  const long long mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // this thread's cp.async requests of a stage: planes (tid >> 5) + 8 r, 16-byte column (tid & 31)
+  auto issue = [&](long long j) {
+    const long long w = blockIdx.x + j * gridDim.x;
+    const int n = (int)(w / chunks_per_n);
+    const long long p0 = (w - (long long)n * chunks_per_n) * GPX + 4 * lane;
+    const long long rem = a.HW - p0;  // pixels left in the plane from this thread's column on
+    const int bytes = rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0);
+    const long long pc = rem > 0 ? p0 : 0;  // keep the (unread) source address inside the tensor
+    float* st = stages + (j % GSTAGES) * (GPLANES * GPS) + 4 * lane;
+#pragma unroll
+    for (int r = 0; r < GPLANES / 8; ++r) {
+      const int pl = warp + 8 * r, which = pl >> 4, ch = pl & 15;  // which: 0 = d_a, 1 = y, 2 = dwo
+      const float* src;
+      bool ok;
+      if (which == 0) { src = a.d_a + (size_t)n * a.da_ss + (size_t)(co0 + ch) * a.HW + pc; ok = ch < nco; }
+      else if (which == 1) { src = a.y + (size_t)n * a.y_ss + (size_t)(co0 + ch) * a.HW + pc; ok = ch < nco; }
+      else { src = a.dwo + ((size_t)n * a.Cin + ci0 + ch) * a.HW + pc; ok = ch < nci; }
+      cp_async16(tma::smem_u32(st + pl * GPS), ok ? src : a.dwo, ok ? bytes : 0);  // zero-fill what is not read
+    }
+  };
+  for (int j = 0; j < GSTAGES - 1; ++j) {
+    if (j < mine) issue(j);
+    cp_async_commit();
+  }
+  for (long long j = 0; j < mine; ++j) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();  // stage j landed for every thread; stage (j - 1) is free again
+    if (j + GSTAGES - 1 < mine) issue(j + GSTAGES - 1);
+    cp_async_commit();
+    const float* st = stages + (j % GSTAGES) * (GPLANES * GPS);
+#pragma unroll
+    for (int u = 0; u < GPX / 64; ++u) {  // 16 k-steps per stage, 2 per warp
+      const int px = (warp * (GPX / 64) + u) * 8 + t;
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // q: 0 = (g, t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
+        const int h = q & 1, e = q >> 1;
+        const float da = st[(g + 8 * h) * GPS + px + 4 * e];
+        const float yv = st[(16 + g + 8 * h) * GPS + px + 4 * e];
+        const float dz = (fmaf(yv, ksc[h], ksh[h]) > klo[h]) ? da : 0.f;
+        // channels past nco have kk* = 0; pixels past HW give dy = k3 but meet a zero-filled dwo
+        tf32_split2(fmaf(kk1[h], dz, fmaf(kk2[h], yv, kk3[h])), ah[q], al[q]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        if (8 * jj >= nci) continue;
+        uint32_t bh0, bl0, bh1, bl1;
+        tf32_split2(st[(32 + 8 * jj + g) * GPS + px], bh0, bl0);      // (k = t,     n = ci 8jj + g)
+        tf32_split2(st[(32 + 8 * jj + g) * GPS + px + 4], bh1, bl1);  // (k = t + 4, n = ci 8jj + g)
+        mma_tf32_16n8k8(c[jj], al, bh0, bh1);
+        mma_tf32_16n8k8(c[jj], ah, bl0, bl1);
+        mma_tf32_16n8k8(c[jj], ah, bh0, bh1);
+      }
+    }
+    if ((j & 3) == 3) {  // keep the tensor core's truncating accumulation chains short (8 k-steps)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ctot[jj][q] += c[jj][q]; c[jj][q] = 0.f; }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float* sred = stages;  // [8][256]
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    sred[warp * 256 + g * 16 + 8 * jj + 2 * t] = ctot[jj][0] + c[jj][0];
+    sred[warp * 256 + g * 16 + 8 * jj + 2 * t + 1] = ctot[jj][1] + c[jj][1];
+    sred[warp * 256 + (g + 8) * 16 + 8 * jj + 2 * t] = ctot[jj][2] + c[jj][2];
+    sred[warp * 256 + (g + 8) * 16 + 8 * jj + 2 * t + 1] = ctot[jj][3] + c[jj][3];
+  }
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += sred[w * 256 + tid];
+  const int o = tid >> 4, ci = tid & 15;
+  if (o < nco && ci < nci) a.partials[((size_t)blockIdx.x * a.Cout + co0 + o) * a.Cin + ci0 + ci] = sum;
+}
+
 }  // namespace
 
 extern "C" {
@@ -678,10 +828,11 @@ int ocrs_det_sep_fwd_rows(int N, int H, int W, int Cout) {
 }
 
 // DepthwiseConv block body (reference models.py:11-22), TMA-pipelined: y = pw1x1(dw3x3(xform(x))) and the
-// BatchNorm partial sums of y. Same contract as ocrs_det_dwpw_fwd except for the partial-row count.
+// BatchNorm partial sums of y. Same contract as ocrs_det_dwpw_fwd except for the partial-row count; when dw_out
+// ([N][Cin][H][W], contiguous) is given, the depthwise output is stored too, for ocrs_det_pw_wgrad_saved.
 int ocrs_det_sep_fwd(const float* x, long long x_ss, int N, int Cin, int H, int W, const float* in_scale,
                      const float* in_shift, const float* in_lo, const float* wdw, const float* wpw, int Cout,
-                     float* y, long long y_ss, float* partials, void* stream) {
+                     float* y, long long y_ss, float* partials, float* dw_out, void* stream) {
   OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "sep_fwd: bad dims");
   OCRS_CHECK_ARG(ocrs_det_tma_supported(x, x_ss, y, y_ss, H, W), "sep_fwd: views are not TMA-addressable");
   const int cot = Cout <= 8 ? 8 : 16;
@@ -689,7 +840,7 @@ int ocrs_det_sep_fwd(const float* x, long long x_ss, int N, int Cin, int H, int 
   FwdArgs a;
   a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.N = N; a.n_cot = ocrs_cdiv(Cout, cot);
   a.in_scale = in_scale; a.in_shift = in_shift; a.in_lo = in_lo; a.wdw = wdw; a.wpw = wpw;
-  a.y = y; a.y_ss = y_ss; a.partials = partials;
+  a.y = y; a.y_ss = y_ss; a.partials = partials; a.dwo = dw_out;
   a.walk.tiles_x = ocrs_cdiv(W, TW); a.walk.tiles_y = ocrs_cdiv(H, TH);
   a.walk.sp_total = N * a.walk.tiles_x * a.walk.tiles_y; a.walk.sp0 = 0; a.walk.sp_stride = 1;
   const int ctas = fwd_ctas(N, H, W, a.n_cot) * a.n_cot;
@@ -782,6 +933,36 @@ int ocrs_det_sep_pw_wgrad(const float* d_a, long long da_ss, const float* y, lon
   dim3 grid(pw_wgrad_workers(N, H, W, pairs), pairs);
   sep_pw_wgrad_tma_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(xmap, a);
   OCRS_CHECK_LAUNCH("sep_pw_wgrad_tma_kernel");
+  return 0;
+}
+
+// Rows of the [workers][Cout][Cin] partials of ocrs_det_pw_wgrad_saved.
+int ocrs_det_pw_wgrad_saved_workers(int N, long long HW, int Cout, int Cin) {
+  const int pairs = ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16);
+  const long long items = (long long)N * ((HW + GPX - 1) / GPX);
+  long long per = (2 * OCRS_NUM_SMS + pairs - 1) / pairs;
+  if (per > items) per = items;
+  return (int)(per < 1 ? 1 : per);
+}
+
+// 1x1-convolution weight gradient from the depthwise output saved by ocrs_det_sep_fwd (dw_out, [N][Cin][HW]
+// contiguous): partials [workers][Cout][Cin] fully written. Needs 16-byte aligned planes (HW % 4 == 0).
+int ocrs_det_pw_wgrad_saved(const float* d_a, long long da_ss, const float* y, long long y_ss, int N, int Cout,
+                            long long HW, const float* sc, const float* sh, const float* lo, const float* k1,
+                            const float* k2, const float* k3, const float* dw_out, int Cin, float* partials,
+                            void* stream) {
+  OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && HW > 0, "pw_wgrad_saved: bad dims");
+  OCRS_CHECK_ARG(HW % 4 == 0 && da_ss % 4 == 0 && y_ss % 4 == 0 && (uintptr_t)d_a % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+                     (uintptr_t)dw_out % 16 == 0, "pw_wgrad_saved: planes must be 16-byte aligned (HW %% 4 == 0)");
+  PwWg2Args a;
+  a.d_a = d_a; a.y = y; a.dwo = dw_out; a.da_ss = da_ss; a.y_ss = y_ss;
+  a.sc = sc; a.sh = sh; a.lo = lo; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.partials = partials;
+  a.Cout = Cout; a.Cin = Cin; a.N = N; a.HW = HW;
+  const size_t smem = (size_t)GSTAGES * GPLANES * GPS * 4;
+  OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ocrs_det_pw_wgrad_saved_workers(N, HW, Cout, Cin), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
+  pw_wgrad_saved_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  OCRS_CHECK_LAUNCH("pw_wgrad_saved_kernel");
   return 0;
 }
 

@@ -21,6 +21,8 @@ NEG_INF = float("-inf")
 # TMA-pipelined DepthwiseConv kernels (csrc/det_tma.cu) wherever the views are TMA-addressable; OCRS_DET_TMA=0 keeps the
 # synchronous tile kernels of det_fwd.cu / det_bwd.cu everywhere (A/B testing; they remain the path for W % 4 != 0).
 USE_TMA = os.environ.get("OCRS_DET_TMA", "1") == "1"
+# Keep each block's depthwise output from the forward pass for its 1x1 weight gradient (OCRS_DET_SAVE_DW=0: recompute it).
+SAVE_DW = os.environ.get("OCRS_DET_SAVE_DW", "1") == "1"
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -75,14 +77,19 @@ class _Sep:
         if y is None:
             y = new_view(N, self.cout, H, W, dev)
         lib = _lib.lib()
+        dwo = None
         tma = (USE_TMA and bool(lib.ocrs_det_tma_supported(inp.p, inp.ss, y.p, y.ss, H, W))
                and bool(lib.ocrs_det_sep_channels_ok(self.cin, self.cout)))
         meta = 4.0 * N * H * W * (self.cin + self.cout)
         if tma:  # TMA-pipelined persistent kernel (csrc/det_tma.cu)
             rows = lib.ocrs_det_sep_fwd_rows(N, H, W, self.cout)
             partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
+            # training: keep the depthwise output for the 1x1 weight gradient (the step is issue-bound, not HBM-bound:
+            # 4*Cin bytes/pixel of extra traffic buy back the stencil recompute in backward)
+            dwo = torch.empty((N, self.cin, H, W), dtype=torch.float32, device=dev) if (save is not None and SAVE_DW) else None
             call("ocrs_det_sep_fwd", inp.p, inp.ss, N, self.cin, H, W, *inp.xfp(), ptr(self.dw.weight),
-                 ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), st, meta=meta)
+                 ptr(self.pw.weight), self.cout, y.p, y.ss, ptr(partials), ptr(dwo), st,
+                 meta=meta + (4.0 * N * H * W * self.cin if dwo is not None else 0.0))
         else:
             rows = lib.ocrs_det_dwpw_partial_rows(N, H, W)
             partials = torch.empty((rows, 2, self.cout), dtype=torch.float32, device=dev) if training else None
@@ -100,7 +107,7 @@ class _Sep:
             bn.num_batches_tracked.add_(1)
         y.xf = xf_dst
         if save is not None:
-            save[id(self)] = (inp, y, stats, bool(training))
+            save[id(self)] = (inp, y, stats, bool(training), dwo)
         return y
 
     def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False, bn_pending=None):
@@ -109,7 +116,7 @@ class _Sep:
         `bn_pending`: dict id(block) -> (partials, rows) of BatchNorm-backward sums already produced by the
         kernel that wrote that block's d_a; this call consumes its own entry and, when its depthwise backward is
         the final writer of the upstream block's d_a (`self.producer`), leaves that block's entry."""
-        inp, y, stats, training = saved.pop(id(self))
+        inp, y, stats, training, dwo = saved.pop(id(self))
         dev = y.t.device
         lib = _lib.lib()
         H, W, HW = y.H, y.W, y.H * y.W
@@ -130,7 +137,13 @@ class _Sep:
         g = new_view(N, ci, H, W, dev)
         call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
              meta=4.0 * N * HW * (2 * co + ci))
-        if USE_TMA and lib.ocrs_det_tma_supported(inp.p, inp.ss, inp.p, inp.ss, H, W):
+        if dwo is not None:
+            workers = lib.ocrs_det_pw_wgrad_saved_workers(N, HW, co, ci)
+            wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+            call("ocrs_det_pw_wgrad_saved", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(dwo), ci, ptr(wpart), st,
+                 meta=4.0 * N * HW * (2 * co + ci))
+            del dwo
+        elif USE_TMA and lib.ocrs_det_tma_supported(inp.p, inp.ss, inp.p, inp.ss, H, W):
             workers = lib.ocrs_det_sep_pw_wgrad_workers(N, H, W, co, ci)
             wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
             call("ocrs_det_sep_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),

@@ -126,6 +126,31 @@ def test_tma_pw_wgrad_matches_fp64(N, cin, cout, H, W):
     assert rel_l2(part.double().sum(0), ref) < 2e-5
 
 
+@pytest.mark.parametrize("N,cin,cout,HW", [(2, 8, 16, 40 * 36), (3, 1, 8, 36 * 45), (1, 32, 16, 1000), (2, 16, 40, 132), (1, 24, 8, 8), (2, 16, 16, 128 * 9)])
+def test_pw_wgrad_from_saved_depthwise_output(N, cin, cout, HW):
+    """ocrs_det_pw_wgrad_saved: both operands streamed in mma fragment layout; any pixel count (tails masked)."""
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200._lib import call, ptr
+
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(cin * 11 + cout)
+    dwo = torch.randn(N, cin, HW, generator=g)
+    y = torch.randn(N, cout, HW, generator=g)
+    d_a = torch.randn(N, cout, HW, generator=g)
+    yxf = _rand_xf(cout, g)
+    k1, k2, k3 = (torch.randn(cout, generator=g) for _ in range(3))
+    act = (y.double() * yxf[0][None, :, None] + yxf[1][None, :, None]) > 0
+    dy = k1[None, :, None] * (d_a.double() * act) + k2[None, :, None] * y.double() + k3[None, :, None]
+    ref = torch.einsum("nop,nip->oi", dy, dwo.double())
+    workers = lib.ocrs_det_pw_wgrad_saved_workers(N, HW, cout, cin)
+    part = torch.full((workers, cout, cin), float("nan"), device="cuda")
+    dev = [t.cuda() for t in (d_a, y, *yxf, k1, k2, k3, dwo)]
+    call("ocrs_det_pw_wgrad_saved", ptr(dev[0]), cout * HW, ptr(dev[1]), cout * HW, N, cout, HW, ptr(dev[2]), ptr(dev[3]), ptr(dev[4]),
+         ptr(dev[5]), ptr(dev[6]), ptr(dev[7]), ptr(dev[8]), cin, ptr(part), _stream())
+    torch.cuda.synchronize()
+    assert rel_l2(part.double().sum(0), ref) < 2e-5
+
+
 @pytest.mark.parametrize("N,C,H,W,acc", [(2, 8, 40, 36, True), (1, 5, 70, 132, False), (2, 16, 32, 64, True), (1, 1, 9, 8, False)])
 def test_tma_dw_bwd_with_fused_upstream_bn_reduction(N, C, H, W, acc):
     """ocrs_det_sep_dw_bwd: dx (accumulated into a strided channel slice), dw weight gradient, and the BatchNorm-backward
