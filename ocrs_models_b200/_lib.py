@@ -44,6 +44,10 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_dw_bwd_rows": [I, I, I],
     "ocrs_det_dw_bwd": [P, L, P, L, I, I, I, I, P, P, P, P, P, L, I, P, P],
     "ocrs_det_pool2_bwd": [P, L, I, I, I, I, P, P, P, P, L, P, L, P],
+    "ocrs_det_pool2_bwd_bn_rows": [I, I, I],
+    "ocrs_det_pool2_bwd_bn": [P, L, I, I, I, I, P, P, P, P, L, P, L, P, P, P, P],
+    "ocrs_det_outconv8_bwd_blocks": [],
+    "ocrs_det_outconv8_bwd_bn": [P, P, P, L, I, L, P, P, P, P, P, L, P, P, P, P, P],
     "ocrs_det_convt_bwd_data": [P, L, I, I, I, I, P, I, I, I, P, L, P],
     "ocrs_det_convt_wgrad_workers": [I, I, I],
     "ocrs_det_convt_wgrad": [P, L, I, I, I, I, P, P, P, P, L, I, I, I, P, P],

@@ -688,6 +688,146 @@ __global__ void pool2_bwd_kernel(const float* __restrict__ x, long long x_ss, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused producers of the BatchNorm-backward sums (sum dz, sum dz * yhat of the block whose activated output these
+// kernels differentiate): the separate bnrelu_bwd_reduce pass over d_a and y is not needed after them.
+
+// MaxPool2d(2) backward + the sums for the block that produced x. partials: [N * gridDim.y * gridDim.x][2][C].
+__global__ void pool2_bwd_bn_kernel(const float* __restrict__ x, long long x_ss, int C, int H, int W,
+                                    const float* __restrict__ sc, const float* __restrict__ sh,
+                                    const float* __restrict__ lo, const float* __restrict__ dout, long long dout_ss,
+                                    float* __restrict__ din, long long din_ss, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, float* __restrict__ partials) {
+  __shared__ float red[32];
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int c = blockIdx.z % C, n = blockIdx.z / C;
+  const int iy = 2 * cy, ix = 2 * cx;
+  const int Ho = H / 2, Wo = W / 2;
+  float s1 = 0.f, s2 = 0.f;
+  if (ix < W && iy < H) {
+    float* dp = din + (size_t)n * din_ss + (size_t)c * H * W + (size_t)iy * W + ix;
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cy < Ho && cx < Wo) {
+      const float* p = x + (size_t)n * x_ss + (size_t)c * H * W + (size_t)iy * W + ix;
+      float raw[4], v[4];
+      if ((W & 1) == 0 && (((uintptr_t)p) & 7) == 0) {
+        const float2 a = *reinterpret_cast<const float2*>(p), b = *reinterpret_cast<const float2*>(p + W);
+        raw[0] = a.x; raw[1] = a.y; raw[2] = b.x; raw[3] = b.y;
+      } else {
+        raw[0] = p[0]; raw[1] = p[1]; raw[2] = p[W]; raw[3] = p[W + 1];
+      }
+      const float s = sc[c], t = sh[c], l = lo[c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = xform_apply(raw[q], s, t, l);
+      int am = 0;
+      float m = v[0], rm = raw[0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q] > m || isnan(v[q])) { m = v[q]; am = q; rm = raw[q]; }
+      const float gv = dout[(size_t)n * dout_ss + (size_t)c * Ho * Wo + (size_t)cy * Wo + cx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] = (q == am) ? gv : 0.f;
+      const float dz = (fmaf(rm, s, t) > l) ? gv : 0.f;  // the only non-zero d_a of the window sits at the arg-max
+      s1 = dz;
+      s2 = dz * (rm - mean[c]) * invstd[c];
+    }
+    const bool x1 = ix + 1 < W, y1 = iy + 1 < H;
+    if (x1 && (W & 1) == 0 && (((uintptr_t)dp) & 7) == 0) {
+      *reinterpret_cast<float2*>(dp) = make_float2(r[0], r[1]);
+      if (y1) *reinterpret_cast<float2*>(dp + W) = make_float2(r[2], r[3]);
+    } else {
+      dp[0] = r[0];
+      if (x1) dp[1] = r[1];
+      if (y1) { dp[W] = r[2]; if (x1) dp[W + 1] = r[3]; }
+    }
+  }
+  // block (32 x 8) reduction; block_sum indexes by threadIdx.x only, so flatten first
+  const int tid = threadIdx.y * 32 + threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) { red[wid] = s1; red[8 + wid] = s2; }
+  __syncthreads();
+  if (tid < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[8 * tid + w];
+    const size_t row = ((size_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    partials[(row * 2 + tid) * C + c] = t;
+  }
+}
+
+// out_conv (C = 8 -> 1) + Sigmoid backward, persistent and vectorised, with the weight/bias partial sums and the
+// BatchNorm-backward sums of the block that produced x in registers for the whole kernel:
+//   wb_partials [gridDim.x][9]: sum_p dz * a[c] (c < 8), sum_p dz;  bn_partials [gridDim.x][2][8].
+__global__ void __launch_bounds__(256)
+outconv8_bwd_bn_kernel(const float* __restrict__ dp, const float* __restrict__ prob, const float* __restrict__ x,
+                       long long x_ss, long long HW, int N, const float* __restrict__ sc,
+                       const float* __restrict__ sh, const float* __restrict__ lo, const float* __restrict__ w,
+                       float* __restrict__ d_a, long long da_ss, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* __restrict__ wb_partials,
+                       float* __restrict__ bn_partials) {
+  constexpr int C = 8;
+  __shared__ float sred[8][32];
+  float acc[32];  // [0..8): dW, 8: dbias, [9..17): sum dz_c, [17..25): sum dz_c * yhat, rest unused
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  float s[C], t[C], l[C], wv[C], mu[C], is[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    s[c] = sc ? sc[c] : 1.f; t[c] = sc ? sh[c] : 0.f; l[c] = sc ? lo[c] : -INFINITY; wv[c] = w[c];
+    mu[c] = mean ? mean[c] : 0.f; is[c] = mean ? invstd[c] : 0.f;
+  }
+  const long long q_per_n = HW / 4, total = q_per_n * N;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < total; q += (long long)gridDim.x * 256) {
+    const int n = (int)(q / q_per_n);
+    const long long i = (q - (long long)n * q_per_n) * 4;
+    const float4 p4 = *reinterpret_cast<const float4*>(prob + (size_t)n * HW + i);
+    const float4 g4 = *reinterpret_cast<const float4*>(dp + (size_t)n * HW + i);
+    const float dz[4] = {g4.x * p4.x * (1.f - p4.x), g4.y * p4.y * (1.f - p4.y), g4.z * p4.z * (1.f - p4.z), g4.w * p4.w * (1.f - p4.w)};
+    acc[8] += (dz[0] + dz[1]) + (dz[2] + dz[3]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 r4 = *reinterpret_cast<const float4*>(x + (size_t)n * x_ss + (size_t)c * HW + i);
+      const float raw[4] = {r4.x, r4.y, r4.z, r4.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pre = fmaf(raw[e], s[c], t[c]);
+        const float a = fmaxf(pre, l[c]);
+        o[e] = wv[c] * dz[e];
+        acc[c] = fmaf(a, dz[e], acc[c]);
+        const float dzc = pre > l[c] ? o[e] : 0.f;
+        acc[9 + c] += dzc;
+        acc[17 + c] = fmaf(dzc, (raw[e] - mu[c]) * is[c], acc[17 + c]);
+      }
+      *reinterpret_cast<float4*>(d_a + (size_t)n * da_ss + (size_t)c * HW + i) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // transposing butterfly: lane j ends with the warp total of acc[j]
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float send = up ? acc[j] : acc[j + o];
+      const float keep = up ? acc[j + o] : acc[j];
+      acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  sred[wid][lane] = acc[0];
+  __syncthreads();
+  if (threadIdx.x < 25) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sred[k][threadIdx.x];
+    const int j = threadIdx.x;
+    if (j < 9) wb_partials[(size_t)blockIdx.x * 9 + j] = v;
+    else if (bn_partials) bn_partials[((size_t)blockIdx.x * 2 + (j >= 17)) * C + (j - 9) % 8] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // ConvTranspose2d backward (data): d_x[ci][iy][ix] = sum_co,k W[ci][co][k] * d_out[co][2iy+ky][2ix+kx].
 template <int CI_T>
@@ -1050,6 +1190,41 @@ int ocrs_det_pool2_bwd(const float* x, long long x_ss, int N, int C, int H, int 
   pool2_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, dout, dout_ss,
                                                              din, din_ss);
   OCRS_CHECK_LAUNCH("pool2_bwd_kernel");
+  return 0;
+}
+
+// Rows of the [rows][2][C] BatchNorm partials ocrs_det_pool2_bwd_bn writes.
+int ocrs_det_pool2_bwd_bn_rows(int N, int H, int W) { return N * ocrs_cdiv((W + 1) / 2, 32) * ocrs_cdiv((H + 1) / 2, 8); }
+
+// ocrs_det_pool2_bwd + the BatchNorm-backward sums (sum dz, sum dz*yhat) of the block that produced x
+// (mean / invstd: that block's batch statistics): replaces ocrs_bnrelu_bwd_reduce for it.
+int ocrs_det_pool2_bwd_bn(const float* x, long long x_ss, int N, int C, int H, int W, const float* sc,
+                          const float* sh, const float* lo, const float* dout, long long dout_ss, float* din,
+                          long long din_ss, const float* mean, const float* invstd, float* bn_partials,
+                          void* stream) {
+  OCRS_CHECK_ARG(sc && mean && invstd && bn_partials, "pool2_bwd_bn: needs the producer's transform and statistics");
+  dim3 block(32, 8), grid(ocrs_cdiv((W + 1) / 2, 32), ocrs_cdiv((H + 1) / 2, 8), N * C);
+  pool2_bwd_bn_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, dout, dout_ss, din,
+                                                                din_ss, mean, invstd, bn_partials);
+  OCRS_CHECK_LAUNCH("pool2_bwd_bn_kernel");
+  return 0;
+}
+
+// Blocks (= partial rows) of ocrs_det_outconv8_bwd_bn.
+int ocrs_det_outconv8_bwd_blocks(void) { return 4 * OCRS_NUM_SMS; }
+
+// out_conv backward for the 8 -> 1 head (reference models.py:126-129), persistent + vectorised, HW % 4 == 0:
+// d_a, weight/bias partials [blocks][9] and, when mean/invstd/bn_partials are given, the BatchNorm-backward sums
+// [blocks][2][8] of the block that produced x.
+int ocrs_det_outconv8_bwd_bn(const float* dp, const float* prob, const float* x, long long x_ss, int N, long long HW,
+                             const float* sc, const float* sh, const float* lo, const float* w, float* d_a,
+                             long long da_ss, const float* mean, const float* invstd, float* wb_partials,
+                             float* bn_partials, void* stream) {
+  OCRS_CHECK_ARG(HW % 4 == 0 && x_ss % 4 == 0 && da_ss % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)d_a % 16 == 0 &&
+                     (uintptr_t)dp % 16 == 0 && (uintptr_t)prob % 16 == 0, "outconv8_bwd_bn: needs 16-byte aligned planes");
+  outconv8_bwd_bn_kernel<<<ocrs_det_outconv8_bwd_blocks(), 256, 0, (cudaStream_t)stream>>>(
+      dp, prob, x, x_ss, HW, N, sc, sh, lo, w, d_a, da_ss, mean, invstd, wb_partials, bn_partials);
+  OCRS_CHECK_LAUNCH("outconv8_bwd_bn_kernel");
   return 0;
 }
 

@@ -21,6 +21,9 @@ NEG_INF = float("-inf")
 # TMA-pipelined DepthwiseConv kernels (csrc/det_tma.cu) wherever the views are TMA-addressable; OCRS_DET_TMA=0 keeps the
 # synchronous tile kernels of det_fwd.cu / det_bwd.cu everywhere (A/B testing; they remain the path for W % 4 != 0).
 USE_TMA = os.environ.get("OCRS_DET_TMA", "1") == "1"
+# BatchNorm-backward sums produced by the kernel that writes d_a (max-pool backward, out_conv backward, depthwise backward)
+# instead of a separate pass over d_a and y; OCRS_DET_FUSE_BN=0 restores the separate ocrs_bnrelu_bwd_reduce everywhere.
+FUSE_BN_REDUCE = os.environ.get("OCRS_DET_FUSE_BN", "1") == "1"
 # Keep each block's depthwise output from the forward pass for its 1x1 weight gradient (OCRS_DET_SAVE_DW=0: recompute it).
 SAVE_DW = os.environ.get("OCRS_DET_SAVE_DW", "1") == "1"
 BN_EPS = 1e-5
@@ -161,7 +164,7 @@ class _Sep:
         if USE_TMA and lib.ocrs_det_tma_supported(g.p, g.ss, inp.p, inp.ss, H, W) and lib.ocrs_det_tma_supported(dx.p, dx.ss, dx.p, dx.ss, H, W):
             drows = lib.ocrs_det_sep_dw_bwd_rows(N, H, W, ci)
             dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
-            up = self.producer if (bn_pending is not None and self.producer is not None and id(self.producer) in saved) else None
+            up = self.producer if (FUSE_BN_REDUCE and bn_pending is not None and self.producer is not None and id(self.producer) in saved) else None
             if up is not None:
                 up_stats = saved[id(up)][2]
                 bnp = torch.empty((drows, 2, ci), dtype=torch.float32, device=dev)
@@ -306,12 +309,24 @@ class _DetFunction(torch.autograd.Function):
                 grads[id(t)] = g
 
         with torch.cuda.device(dev):
-            # out_conv + sigmoid
-            rows = lib.ocrs_det_outconv_bwd_rows(N, H, W)
-            part = torch.empty((rows, d[0] + 1), dtype=torch.float32, device=dev)
+            # out_conv + sigmoid (+ the BatchNorm-backward sums of the block feeding it)
             d_a = new_view(N, d[0], H, W, dev)
-            call("ocrs_det_outconv_bwd", ptr(dprob), ptr(prob), last.p, last.ss, N, d[0], H, W, *last.xfp(),
-                 ptr(plan.out.weight), d_a.p, d_a.ss, ptr(part), st)
+            last_blk = plan.contract[0][1]
+            if FUSE_BN_REDUCE and d[0] == 8 and (H * W) % 4 == 0 and id(last_blk) in recs and last.xf is not None:
+                blocks = lib.ocrs_det_outconv8_bwd_blocks()
+                part = torch.empty((blocks, d[0] + 1), dtype=torch.float32, device=dev)
+                bnp = torch.empty((blocks, 2, d[0]), dtype=torch.float32, device=dev)
+                st_last = recs[id(last_blk)][2]
+                call("ocrs_det_outconv8_bwd_bn", ptr(dprob), ptr(prob), last.p, last.ss, N, H * W, *last.xfp(),
+                     ptr(plan.out.weight), d_a.p, d_a.ss, ptr(st_last[0]), ptr(st_last[1]), ptr(part), ptr(bnp), st,
+                     meta=4.0 * N * H * W * (2 + 2 * d[0]))
+                pend[id(last_blk)] = (bnp, blocks)
+                rows = blocks
+            else:
+                rows = lib.ocrs_det_outconv_bwd_rows(N, H, W)
+                part = torch.empty((rows, d[0] + 1), dtype=torch.float32, device=dev)
+                call("ocrs_det_outconv_bwd", ptr(dprob), ptr(prob), last.p, last.ss, N, d[0], H, W, *last.xfp(),
+                     ptr(plan.out.weight), d_a.p, d_a.ss, ptr(part), st)
             wb = torch.empty((d[0] + 1,), dtype=torch.float32, device=dev)
             _finalize(part, rows, d[0] + 1, wb, st)
             put([plan.out.weight, plan.out.bias], [wb[: d[0]].reshape(1, d[0], 1, 1).clone(), wb[d[0] :].clone()])
@@ -350,8 +365,17 @@ class _DetFunction(torch.autograd.Function):
             for i in reversed(range(L)):
                 b = pooled_src[i]
                 d_full = new_view(N, b.C, b.H, b.W, dev)
-                call("ocrs_det_pool2_bwd", b.p, b.ss, N, b.C, b.H, b.W, *b.xfp(), d_pooled.p, d_pooled.ss,
-                     d_full.p, d_full.ss, st)
+                blk = plan.down[i][1]
+                if FUSE_BN_REDUCE and id(blk) in recs and b.xf is not None:
+                    prow = lib.ocrs_det_pool2_bwd_bn_rows(N, b.H, b.W)
+                    bnp = torch.empty((prow, 2, b.C), dtype=torch.float32, device=dev)
+                    st_b = recs[id(blk)][2]
+                    call("ocrs_det_pool2_bwd_bn", b.p, b.ss, N, b.C, b.H, b.W, *b.xfp(), d_pooled.p, d_pooled.ss,
+                         d_full.p, d_full.ss, ptr(st_b[0]), ptr(st_b[1]), ptr(bnp), st)
+                    pend[id(blk)] = (bnp, prow)
+                else:
+                    call("ocrs_det_pool2_bwd", b.p, b.ss, N, b.C, b.H, b.W, *b.xfp(), d_pooled.p, d_pooled.ss,
+                         d_full.p, d_full.ss, st)
                 gB, d_mid = plan.down[i][1].backward(recs, d_full, N, st, None, bn_pending=pend)
                 put(plan.down[i][1].params(), gB)
                 # input of down[i] is the skip half of cat[i]; its gradient already holds the Up-path part
