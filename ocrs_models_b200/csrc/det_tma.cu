@@ -687,6 +687,10 @@ struct PwWg2Args {
   float* partials;  // [gridDim.x][Cout][Cin]
   int Cout, Cin, N;
   long long HW;
+  // optional fused 1x1 data gradient g[ci][p] = sum_co Wpw[co][ci] * dy[co][p] (Cout <= 16 only): the staged d_a / y
+  // tile is already in shared memory, so ocrs_det_pwT_bwd's second pass over d_a and y disappears
+  const float* wpw;  // [Cout][Cin] or null
+  float* g; long long g_ss;
 };
 // Operands are staged by cp.async.cg (16 bytes = 4 pixels of one channel plane per request: every warp request
 // covers 512 contiguous bytes of ONE plane, where gathering straight in fragment layout touched 8 planes per
@@ -708,10 +712,25 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 pw_wgrad_saved_kernel(PwWg2Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);  // [GSTAGES][GPLANES][GPS]; reused for the final reduction
+  float* gs = stages + GSTAGES * GPLANES * GPS;        // [16][GPS] staging of the fused data gradient
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int cit = (a.Cin + 15) / 16;
   const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
   const int nco = min(16, a.Cout - co0), nci = min(16, a.Cin - ci0);
+  const bool do_g = a.wpw != nullptr;  // host guarantees Cout <= 16, i.e. co0 == 0
+  // A fragments of the g-mma (M = ci, K = co with the slot permutation k = t -> co 2t, k = t + 4 -> co 2t + 1, which
+  // makes the B reads below bank-conflict free): a0 (ci g, co 2t), a1 (ci g+8, co 2t), a2 (ci g, co 2t+1), a3 (ci g+8, co 2t+1)
+  uint32_t wh[2][4], wl[2][4];
+  if (do_g) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ci = g + 8 * (q & 1), co = 8 * ks + 2 * t + (q >> 1);
+        const float v = (ci < nci && co < nco) ? a.wpw[(size_t)co * a.Cin + ci0 + ci] : 0.f;
+        tf32_split2(v, wh[ks][q], wl[ks][q]);
+      }
+  }
   float ksc[2], ksh[2], klo[2], kk1[2], kk2[2], kk3[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -757,9 +776,9 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
     __syncthreads();  // stage j landed for every thread; stage (j - 1) is free again
     if (j + GSTAGES - 1 < mine) issue(j + GSTAGES - 1);
     cp_async_commit();
-    const float* st = stages + (j % GSTAGES) * (GPLANES * GPS);
+    float* st = stages + (j % GSTAGES) * (GPLANES * GPS);
 #pragma unroll
-    for (int u = 0; u < GPX / 64; ++u) {  // 16 k-steps per stage, 2 per warp
+    for (int u = 0; u < GPX / 64; ++u) {  // 16 k-steps per stage, 2 per warp: warp w owns pixels 16w .. 16w+15
       const int px = (warp * (GPX / 64) + u) * 8 + t;
       uint32_t ah[4], al[4];
 #pragma unroll
@@ -769,7 +788,9 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
         const float yv = st[(16 + g + 8 * h) * GPS + px + 4 * e];
         const float dz = (fmaf(yv, ksc[h], ksh[h]) > klo[h]) ? da : 0.f;
         // channels past nco have kk* = 0; pixels past HW give dy = k3 but meet a zero-filled dwo
-        tf32_split2(fmaf(kk1[h], dz, fmaf(kk2[h], yv, kk3[h])), ah[q], al[q]);
+        const float dy = fmaf(kk1[h], dz, fmaf(kk2[h], yv, kk3[h]));
+        tf32_split2(dy, ah[q], al[q]);
+        if (do_g) st[(g + 8 * h) * GPS + px + 4 * e] = dy;  // in place over d_a: only this warp reads these pixels
       }
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
@@ -780,6 +801,44 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
         mma_tf32_16n8k8(c[jj], al, bh0, bh1);
         mma_tf32_16n8k8(c[jj], ah, bl0, bl1);
         mma_tf32_16n8k8(c[jj], ah, bh0, bh1);
+      }
+    }
+    if (do_g) {
+      // g tile of this stage: warp w owns pixels 16w .. 16w+15 (two n-tiles of 8), all 16 input channels
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int px = warp * 16 + nt * 8;
+        float cg[4] = {0.f, 0.f, 0.f, 0.f}, cx[4] = {0.f, 0.f, 0.f, 0.f};  // hi.hi and cross terms apart
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          if (8 * ks >= nco) continue;
+          uint32_t bh[2], bl[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e)  // B: (k = t -> co 2t, k = t+4 -> co 2t+1; n = pixel g): dy written above
+            tf32_split2(st[(8 * ks + 2 * t + e) * GPS + px + g], bh[e], bl[e]);
+          mma_tf32_16n8k8(cx, wl[ks], bh[0], bh[1]);
+          mma_tf32_16n8k8(cx, wh[ks], bl[0], bl[1]);
+          mma_tf32_16n8k8(cg, wh[ks], bh[0], bh[1]);
+        }
+        // C fragment: c0 (ci g, px 2t), c1 (ci g, px 2t+1), c2 (ci g+8, px 2t), c3 (ci g+8, px 2t+1)
+        *reinterpret_cast<float2*>(gs + g * GPS + px + 2 * t) = make_float2(cg[0] + cx[0], cg[1] + cx[1]);
+        *reinterpret_cast<float2*>(gs + (g + 8) * GPS + px + 2 * t) = make_float2(cg[2] + cx[2], cg[3] + cx[3]);
+      }
+      __syncthreads();  // gs complete (the loop-top barrier of the next stage protects its reuse)
+      {
+        const long long w = blockIdx.x + j * gridDim.x;
+        const int n = (int)(w / chunks_per_n);
+        const long long p0 = (w - (long long)n * chunks_per_n) * GPX + 4 * lane;
+        if (p0 < a.HW) {  // HW % 4 == 0: the four pixels are in or out together
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int ci = warp + 8 * r;
+            if (ci < nci)
+              *reinterpret_cast<float4*>(a.g + (size_t)n * a.g_ss + (size_t)(ci0 + ci) * a.HW + p0) =
+                  *reinterpret_cast<const float4*>(gs + ci * GPS + 4 * lane);
+          }
+        }
       }
     }
     if ((j & 3) == 3) {  // keep the tensor core's truncating accumulation chains short (8 k-steps)
@@ -947,18 +1006,23 @@ int ocrs_det_pw_wgrad_saved_workers(int N, long long HW, int Cout, int Cin) {
 
 // 1x1-convolution weight gradient from the depthwise output saved by ocrs_det_sep_fwd (dw_out, [N][Cin][HW]
 // contiguous): partials [workers][Cout][Cin] fully written. Needs 16-byte aligned planes (HW % 4 == 0).
+// With wpw ([Cout][Cin], Cout <= 16) it also writes the 1x1 data gradient g[ci][p] = sum_co wpw[co][ci] * dy[co][p]
+// (what ocrs_det_pwT_bwd computes) from the same staged tile.
 int ocrs_det_pw_wgrad_saved(const float* d_a, long long da_ss, const float* y, long long y_ss, int N, int Cout,
                             long long HW, const float* sc, const float* sh, const float* lo, const float* k1,
                             const float* k2, const float* k3, const float* dw_out, int Cin, float* partials,
-                            void* stream) {
+                            const float* wpw, float* g, long long g_ss, void* stream) {
   OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && HW > 0, "pw_wgrad_saved: bad dims");
+  OCRS_CHECK_ARG(wpw == nullptr || (Cout <= 16 && g != nullptr && g_ss % 4 == 0 && (uintptr_t)g % 16 == 0),
+                 "pw_wgrad_saved: the fused data gradient needs Cout <= 16 and a 16-byte aligned g");
   OCRS_CHECK_ARG(HW % 4 == 0 && da_ss % 4 == 0 && y_ss % 4 == 0 && (uintptr_t)d_a % 16 == 0 && (uintptr_t)y % 16 == 0 &&
                      (uintptr_t)dw_out % 16 == 0, "pw_wgrad_saved: planes must be 16-byte aligned (HW %% 4 == 0)");
   PwWg2Args a;
   a.d_a = d_a; a.y = y; a.dwo = dw_out; a.da_ss = da_ss; a.y_ss = y_ss;
   a.sc = sc; a.sh = sh; a.lo = lo; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.partials = partials;
   a.Cout = Cout; a.Cin = Cin; a.N = N; a.HW = HW;
-  const size_t smem = (size_t)GSTAGES * GPLANES * GPS * 4;
+  a.wpw = wpw; a.g = g; a.g_ss = g_ss;
+  const size_t smem = (size_t)GSTAGES * GPLANES * GPS * 4 + 16 * GPS * 4;
   OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ocrs_det_pw_wgrad_saved_workers(N, HW, Cout, Cin), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
   pw_wgrad_saved_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);

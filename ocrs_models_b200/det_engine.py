@@ -24,6 +24,8 @@ USE_TMA = os.environ.get("OCRS_DET_TMA", "1") == "1"
 # BatchNorm-backward sums produced by the kernel that writes d_a (max-pool backward, out_conv backward, depthwise backward)
 # instead of a separate pass over d_a and y; OCRS_DET_FUSE_BN=0 restores the separate ocrs_bnrelu_bwd_reduce everywhere.
 FUSE_BN_REDUCE = os.environ.get("OCRS_DET_FUSE_BN", "1") == "1"
+# 1x1 data gradient computed inside the weight-gradient kernel for blocks with <= 16 output channels (OCRS_DET_FUSE_PWT=0: separate pass).
+FUSE_PWT = os.environ.get("OCRS_DET_FUSE_PWT", "1") == "1"
 # Keep each block's depthwise output from the forward pass for its 1x1 weight gradient (OCRS_DET_SAVE_DW=0: recompute it).
 SAVE_DW = os.environ.get("OCRS_DET_SAVE_DW", "1") == "1"
 BN_EPS = 1e-5
@@ -138,13 +140,16 @@ class _Sep:
              ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), int(training), st)
         k = (ysc, ysh, ylo, ptr(coef[2]), ptr(coef[3]), ptr(coef[4]))
         g = new_view(N, ci, H, W, dev)
-        call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
-             meta=4.0 * N * HW * (2 * co + ci))
+        fuse_g = dwo is not None and co <= 16 and FUSE_PWT  # the weight-gradient kernel also emits g (csrc/det_tma.cu)
+        if not fuse_g:
+            call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
+                 meta=4.0 * N * HW * (2 * co + ci))
         if dwo is not None:
             workers = lib.ocrs_det_pw_wgrad_saved_workers(N, HW, co, ci)
             wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
-            call("ocrs_det_pw_wgrad_saved", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(dwo), ci, ptr(wpart), st,
-                 meta=4.0 * N * HW * (2 * co + ci))
+            call("ocrs_det_pw_wgrad_saved", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(dwo), ci, ptr(wpart),
+                 ptr(self.pw.weight) if fuse_g else None, g.p if fuse_g else None, g.ss, st,
+                 meta=4.0 * N * HW * (2 * co + ci + (ci if fuse_g else 0)))
             del dwo
         elif USE_TMA and lib.ocrs_det_tma_supported(inp.p, inp.ss, inp.p, inp.ss, H, W):
             workers = lib.ocrs_det_sep_pw_wgrad_workers(N, H, W, co, ci)

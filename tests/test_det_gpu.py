@@ -145,10 +145,17 @@ def test_pw_wgrad_from_saved_depthwise_output(N, cin, cout, HW):
     workers = lib.ocrs_det_pw_wgrad_saved_workers(N, HW, cout, cin)
     part = torch.full((workers, cout, cin), float("nan"), device="cuda")
     dev = [t.cuda() for t in (d_a, y, *yxf, k1, k2, k3, dwo)]
+    wpw = torch.randn(cout, cin, generator=g)
+    fuse = cout <= 16
+    gout = torch.full((N, cin, HW), float("nan"), device="cuda")
+    wd = wpw.cuda()
     call("ocrs_det_pw_wgrad_saved", ptr(dev[0]), cout * HW, ptr(dev[1]), cout * HW, N, cout, HW, ptr(dev[2]), ptr(dev[3]), ptr(dev[4]),
-         ptr(dev[5]), ptr(dev[6]), ptr(dev[7]), ptr(dev[8]), cin, ptr(part), _stream())
+         ptr(dev[5]), ptr(dev[6]), ptr(dev[7]), ptr(dev[8]), cin, ptr(part), ptr(wd) if fuse else None, ptr(gout) if fuse else None,
+         cin * HW, _stream())
     torch.cuda.synchronize()
     assert rel_l2(part.double().sum(0), ref) < 2e-5
+    if fuse:  # fused 1x1 data gradient
+        assert rel_l2(gout, torch.einsum("oi,nop->nip", wpw.double(), dy)) < 2e-6
 
 
 @pytest.mark.parametrize("N,C,H,W,acc", [(2, 8, 40, 36, True), (1, 5, 70, 132, False), (2, 16, 32, 64, True), (1, 1, 9, 8, False)])
