@@ -185,6 +185,8 @@ def kernel_profile(wl: Workload, steps=2):
 KERNEL_OF = {"ocrs_gemm_tc": "gemm_tc_kernel", "ocrs_conv3x3_tc": "gemm_tc_kernel", "ocrs_conv3x3_wgrad_tc": "gemm_tc_kernel",
              "ocrs_gemm_tc_presplit": "gemm_tc_kernel", "ocrs_conv3x3_tc_presplit": "gemm_tc_kernel",
              "ocrs_gemm": "gemm_kernel", "ocrs_det_pw_wgrad": "pw_wgrad_mma_kernel", "ocrs_det_dwpw_fwd": "dwpw_fwd_kernel",
+             "ocrs_det_sep_fwd": "sep_fwd_tma_kernel", "ocrs_det_sep_dw_bwd": "sep_dw_bwd_tma_kernel",
+             "ocrs_det_pw_wgrad_saved": "pw_wgrad_saved_kernel", "ocrs_det_sep_pw_wgrad": "sep_pw_wgrad_tma_kernel",
              "ocrs_det_dw_bwd": "dw_bwd_kernel", "ocrs_det_pwT_bwd": "pwT_bwd_kernel",
              "ocrs_bnrelu_bwd_reduce": "bnrelu_bwd_reduce_kernel", "ocrs_det_convt_wgrad": "convt_wgrad_mma_kernel",
              "ocrs_gru_layer_fwd_persist": "gru_fwd_persist_kernel", "ocrs_gru_layer_bwd_persist": "gru_bwd_persist_kernel"}

@@ -764,9 +764,15 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
       if (which == 0) { src = a.d_a + (size_t)n * a.da_ss + (size_t)(co0 + ch) * a.HW + pc; ok = ch < nco; }
       else if (which == 1) { src = a.y + (size_t)n * a.y_ss + (size_t)(co0 + ch) * a.HW + pc; ok = ch < nco; }
       else { src = a.dwo + ((size_t)n * a.Cin + ci0 + ch) * a.HW + pc; ok = ch < nci; }
-      cp_async16(tma::smem_u32(st + pl * GPS), ok ? src : a.dwo, ok ? bytes : 0);  // zero-fill what is not read
+      if (ok) cp_async16(tma::smem_u32(st + pl * GPS), src, bytes);  // bytes < 16 zero-fills the tail of a plane
     }
   };
+  // planes of channels this CTA does not have (8-channel blocks, Cin = 1) are zeroed once and never requested
+  for (int i = tid; i < GSTAGES * GPLANES * GPS; i += NTHREADS) {
+    const int pl = (i / GPS) % GPLANES, ch = pl & 15;
+    if (ch >= ((pl >> 4) == 2 ? nci : nco)) stages[i] = 0.f;
+  }
+  __syncthreads();
   for (int j = 0; j < GSTAGES - 1; ++j) {
     if (j < mine) issue(j);
     cp_async_commit();
@@ -784,6 +790,7 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // q: 0 = (g, t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
         const int h = q & 1, e = q >> 1;
+        if (8 * h >= nco) { ah[q] = 0u; al[q] = 0u; continue; }  // uniform: 8-channel blocks use half of the M tile
         const float da = st[(g + 8 * h) * GPS + px + 4 * e];
         const float yv = st[(16 + g + 8 * h) * GPS + px + 4 * e];
         const float dz = (fmaf(yv, ksc[h], ksh[h]) > klo[h]) ? da : 0.f;
