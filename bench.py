@@ -98,7 +98,7 @@ def make_batch(kind: str, rank: int, device, n: int | None = None):
 class Workload:
     """Model + fused optimiser + one synthetic batch (pinned on the host, resident on the device)."""
 
-    def __init__(self, kind, device, rank, world, group=None):
+    def __init__(self, kind, device, rank, world, group=None, n=None):
         from ocrs_models_b200 import CTCLoss, DetectionModel, RecognitionModel, balanced_cross_entropy_loss
         from ocrs_models_b200.optim import FusedAdam
         from ocrs_models_b200.alphabet import DEFAULT_ALPHABET
@@ -113,7 +113,7 @@ class Workload:
             self.model = DetectionModel().to(device).train()
             self.opt = FusedAdam(self.model, lr=1e-3, process_group=group, world_size=world)
             self.loss_fn = balanced_cross_entropy_loss
-        self.host = {k: v.pin_memory() for k, v in make_batch(kind, rank, device).items()}
+        self.host = {k: v.pin_memory() for k, v in make_batch(kind, rank, device, n).items()}
         self.dev = {k: v.to(device) for k, v in self.host.items()}
         self.units = self.host["image"].shape[0]
         self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in self.host.items() if k in ("image", "mask", "targets"))
@@ -399,6 +399,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def strong_scaling(args, device, rank, world, dist_on, global_batch=512):
+    """BASELINE configs[3]: recognition at a FIXED global batch of 512 lines split over the ranks (strong scaling), next to
+    the weak-scaling headline (64 lines per GPU). Same step, device-timed, max over ranks."""
+    per = global_batch // world
+    wl = Workload("rec", device, rank, world, n=per)
+    steps = max(3, min(args.steps, 10))
+    ms, _ = timed(wl.step_resident, steps, 3, device, dist_on)
+    del wl
+    torch.cuda.empty_cache()
+    return {"metric": "train lines/sec rec@64x800, global batch 512 (strong scaling)", "global_batch": per * world,
+            "per_gpu_batch": per, "value": per * world * steps / (ms * 1e-3), "unit": "lines/s", "ms_per_step": ms / steps,
+            "steps": steps, "scaling": "strong"}
+
+
 def metric_name(kind):
     return "train lines/sec rec@64x800" if kind == "rec" else "train images/sec det@1024x1024"
 
@@ -495,6 +509,7 @@ def main():
     other = "det" if args.workload == "rec" else "rec"
     other_res = None if args.no_secondary else measure(other, args, device, rank, world, dist_on, pk)
 
+    strong = None if (args.no_secondary or args.workload != "rec") else strong_scaling(args, device, rank, world, dist_on)
     if rank == 0:
         line = {
             "metric": metric_name(args.workload),
@@ -509,6 +524,8 @@ def main():
             "ctc_roofline": main_res.get("ctc_roofline"),
             "kernel_ms_per_step": main_res.get("kernel_ms_per_step"),
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
         if other_res is not None:
             line[other] = {"metric": metric_name(other),
                            "workload": workload_name(other), **other_res}

@@ -95,6 +95,9 @@ SIGNATURES: dict[str, list] = {
     "ocrs_log_softmax_fwd": [P, P, I, I, P],
     "ocrs_log_softmax_bwd": [P, P, P, I, I, P],
     "ocrs_transpose": [P, P, I, I, P],
+    # recognition accuracy bookkeeping (csrc/metrics.cu)
+    "ocrs_ctc_greedy_cer_max_targets": [],
+    "ocrs_ctc_greedy_cer": [P, I, I, I, P, P, L, I, I, P, P, P, P, P],
     # optimiser glue (csrc/optim.cu)
     "ocrs_optim_blocks": [],
     "ocrs_grad_norm": [P, L, F, P, P, P],

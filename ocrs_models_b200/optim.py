@@ -64,12 +64,26 @@ class FusedAdam:
 
     def zero_grad(self):
         self.flat_g.zero_()
+        self._synced = False
+
+    def sync_gradients(self) -> torch.Tensor:
+        """The data-path collective of the step: SUM the flat gradient bucket over the ranks (once per step; `step()`
+        calls it if the caller did not). Returns the bucket, which then holds world * (mean gradient): the 1/world
+        factor is applied inside the clip/Adam kernels (`grad_scale`), not by another pass over the bucket."""
+        if self.world > 1 and not getattr(self, "_synced", False):
+            allreduce_sum_(self.flat_g, self.group)
+        self._synced = True
+        return self.flat_g
+
+    def averaged_gradients(self) -> dict:
+        """name-less view for tests: list of (parameter, averaged gradient) after `sync_gradients()`."""
+        self.sync_gradients()
+        return [(p, p.grad / self.world) for p in self.params]
 
     def step(self):
         """Returns the (device) gradient-norm tensor when clipping is on, else None."""
         st = _lib.stream_ptr(self.dev)
-        if self.world > 1:
-            allreduce_sum_(self.flat_g, self.group)
+        self.sync_gradients()
         scale = 1.0 / self.world
         self.t += 1
         clip = self.max_grad_norm if self.max_grad_norm is not None else -1.0

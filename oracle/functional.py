@@ -234,6 +234,47 @@ def ctc_nll_numpy(log_probs: np.ndarray, target: np.ndarray, input_len: int, bla
 
 
 # ------------------------------------------------------------------------------------------
+# recognition accuracy bookkeeping (train_rec.py:29-68, datasets/util.py:132-177, pylev.levenshtein)
+
+
+def ctc_greedy_decode_labels(frame_labels) -> list[int]:
+    """datasets/util.py:163-177 on label level: skip repeats of the previous frame's label, then blanks (0)."""
+    out, last = [], None
+    for c in frame_labels:
+        if c == last:
+            continue
+        last = c
+        if c == 0:
+            continue
+        out.append(int(c))
+    return out
+
+
+def levenshtein(a, b) -> int:
+    """Edit distance (insert / delete / substitute, unit costs) as computed by pylev.levenshtein (train_rec.py:64)."""
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def greedy_cer(preds: torch.Tensor, pred_lengths, targets: torch.Tensor):
+    """RecognitionAccuracyStats.update (train_rec.py:29-68) per sample: ([edit distances], [decoded label lists]).
+    preds [T, N, C]; targets [N, S_pad] (decode_text, util.py:135-147, keeps every label > 0 of the padded row)."""
+    labels = preds.argmax(-1).transpose(0, 1).tolist()
+    dists, decs = [], []
+    for y, x, x_len in zip(targets.tolist(), labels, [int(v) for v in pred_lengths]):
+        tgt = [c for c in y if c > 0]
+        dec = ctc_greedy_decode_labels(x[:x_len])
+        dists.append(levenshtein(tgt, dec))
+        decs.append(dec)
+    return dists, decs
+
+
+# ------------------------------------------------------------------------------------------
 # optimiser glue (train_detection.py:378, train_rec.py:148,381-382)
 
 

@@ -150,3 +150,34 @@ def test_bench_first_step_constants_present():
     assert np.isfinite([c["rec_loss_f64"], c["det_loss_f64"]]).all()
     assert abs(c["rec_loss_f32"] - c["rec_loss_f64"]) < 1e-4 * c["rec_loss_f64"]
     assert abs(c["det_loss_f32"] - c["det_loss_f64"]) < 1e-4 * c["det_loss_f64"]
+
+
+def test_greedy_cer_oracle_matches_the_reference_functions():
+    """oracle.greedy_cer vs the reference's own decode_text / ctc_greedy_decode_text (datasets/util.py) + Levenshtein."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from baseline import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref not staged")
+    ref_loader.load()
+    from ocrs_models.datasets.util import ctc_greedy_decode_text, decode_text
+    from ocrs_models.train_rec import levenshtein  # pylev (or its stand-in under baseline/stubs)
+
+    alphabet = list(O.DEFAULT_ALPHABET)
+    g = torch.Generator().manual_seed(0)
+    T, N, C, S = 50, 6, 97, 16
+    lp = torch.randn(T, N, C, generator=g)
+    runs = torch.randint(0, C, (T // 2, N), generator=g).repeat_interleave(2, dim=0)
+    lp.scatter_(2, runs.unsqueeze(-1), 8.0)
+    tg = torch.randint(0, C, (N, S), generator=g, dtype=torch.int32)
+    pl = torch.tensor([50, 40, 0, 13, 50, 1])
+    dists, decs = O.greedy_cer(lp, pl, tg)
+    labels = lp.argmax(-1).transpose(0, 1).tolist()
+    for n in range(N):
+        t_text, p_text = decode_text(tg[n].tolist(), alphabet), ctc_greedy_decode_text(labels[n][: int(pl[n])], alphabet)
+        assert "".join(alphabet[c - 1] for c in decs[n]) == p_text
+        assert dists[n] == levenshtein(t_text, p_text)
+    assert O.levenshtein("kitten", "sitting") == 3 and O.levenshtein("", "abc") == 3
