@@ -98,6 +98,8 @@ SIGNATURES: dict[str, list] = {
     # recognition accuracy bookkeeping (csrc/metrics.cu)
     "ocrs_ctc_greedy_cer_max_targets": [],
     "ocrs_ctc_greedy_cer": [P, I, I, I, P, P, L, I, I, P, P, P, P, P],
+    # input pipeline (csrc/data.cu)
+    "ocrs_collate_lines": [P, I, P, P, I, I, I, P, P],
     # optimiser glue (csrc/optim.cu)
     "ocrs_optim_blocks": [],
     "ocrs_grad_norm": [P, L, F, P, P, P],
