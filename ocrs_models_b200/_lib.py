@@ -63,6 +63,9 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_sep_dw_bwd": [P, L, P, L, I, I, I, I, P, P, P, P, P, L, I, P, P, P, P, P],
     "ocrs_det_sep_pw_wgrad_workers": [I, I, I, I, I],
     "ocrs_det_sep_pw_wgrad": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, L, I, P, P, P, P, P, P],
+    "ocrs_det_convt_wgrad_staged_ok": [P, L, I, I, P, L, I, I],
+    "ocrs_det_convt_wgrad_staged_workers": [I, I, I, I, I],
+    "ocrs_det_convt_wgrad_staged": [P, L, I, I, I, I, P, P, P, P, L, I, I, I, P, P],
     # GEMM / im2col (csrc/gemm.cu)
     "ocrs_gemm_stat_rows": [I],
     "ocrs_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],

@@ -873,6 +873,155 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
   if (o < nco && ci < nci) a.partials[((size_t)blockIdx.x * a.Cout + co0 + o) * a.Cin + ci0 + ci] = sum;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// ConvTranspose2d(k3, s2) weight gradient (reference models.py:76-78):
+//   dW[ci][co][ky][kx] = sum_{n,iy,ix} xact[n][ci][iy][ix] * dout[n][co][2iy+ky][2ix+kx]
+// = nine skinny GEMMs that share the A operand (xact, M = 16 input channels, K = input pixels) and take their B
+// operands from nine stride-2 views of the same dout tile. The tile (4 input rows x 64 input columns of 16 input
+// channels; 9 x 132 output pixels of 8 output channels) is staged by cp.async in plane-contiguous 16-byte
+// requests (2-stage ring); fragments come from shared memory; mma.sync m16n8k8 3xTF32 like the 1x1 kernels.
+// The old kernel gathered both operands from global memory in fragment layout (8 planes and stride-2 columns per
+// warp request) and re-read x once per 16 (co, tap) pairs.
+constexpr int CTR = 4, CTC = 64;             // input rows / columns per tile
+constexpr int CT_XPS = CTR * CTC + 4;        // x plane stride (260 = 4 mod 32: conflict-free A fragments)
+constexpr int CT_DROWS = 2 * CTR + 1;        // dout rows per tile
+constexpr int CT_DCOLS = 2 * CTC + 4;        // dout columns per tile (129 used, 16-byte multiple)
+constexpr int CT_DPS = CT_DROWS * CT_DCOLS + 8;   // dout plane stride
+constexpr int CT_STAGE = 16 * CT_XPS + 8 * CT_DPS;
+
+struct ConvtWgArgs {
+  const float *x, *dout;
+  long long x_ss, dout_ss;
+  const float *isc, *ish, *ilo;
+  float* partials;  // [gridDim.x][Cin][Cout][9]
+  int Cin, Cout, Hin, Win, Hs, Ws, N;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+convt_wgrad_staged_kernel(ConvtWgArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);  // [2][CT_STAGE]; reused for the final reduction
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cot = (a.Cout + 7) / 8;
+  const int ci0 = (blockIdx.y / cot) * 16, co0 = (blockIdx.y % cot) * 8;
+  const int nci = min(16, a.Cin - ci0), nco = min(8, a.Cout - co0);
+  float sc[2], sh[2], lo[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const bool v = g + 8 * h < nci && a.isc != nullptr;
+    sc[h] = v ? a.isc[ci0 + g + 8 * h] : 1.f;
+    sh[h] = v ? a.ish[ci0 + g + 8 * h] : 0.f;
+    lo[h] = v ? a.ilo[ci0 + g + 8 * h] : -INFINITY;
+  }
+  const int tiles_x = (a.Win + CTC - 1) / CTC, tiles_y = (a.Hin + CTR - 1) / CTR;
+  const long long total = (long long)a.N * tiles_x * tiles_y;
+  const long long mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto decode = [&](long long j, int& n, int& ix0, int& iy0) {
+    const long long w = blockIdx.x + j * gridDim.x;
+    n = (int)(w / (tiles_x * tiles_y));
+    const int r = (int)(w - (long long)n * tiles_x * tiles_y);
+    iy0 = (r / tiles_x) * CTR;
+    ix0 = (r % tiles_x) * CTC;
+  };
+  auto issue = [&](long long j) {
+    int n, ix0, iy0;
+    decode(j, n, ix0, iy0);
+    float* st = stages + (j & 1) * CT_STAGE;
+    // x: nci planes x CTR rows x 16 requests; requests past the image are zero-filled (src_bytes 0)
+    for (int e = tid; e < nci * CTR * (CTC / 4); e += NTHREADS) {
+      const int c = e / (CTR * (CTC / 4)), r = (e / (CTC / 4)) % CTR, q = e % (CTC / 4);
+      const int iy = iy0 + r, ix = ix0 + 4 * q;
+      const bool ok = iy < a.Hin && ix < a.Win;  // Win % 4 == 0: a request is inside or outside as a whole
+      const float* src = a.x + (size_t)n * a.x_ss + ((size_t)(ci0 + c) * a.Hin + (ok ? iy : 0)) * a.Win + (ok ? ix : 0);
+      cp_async16(tma::smem_u32(st + c * CT_XPS + r * CTC + 4 * q), src, ok ? 16 : 0);
+    }
+    // dout: nco planes x 9 rows x 33 requests starting at (2 iy0, 2 ix0)
+    float* sd = st + 16 * CT_XPS;
+    for (int e = tid; e < nco * CT_DROWS * (CT_DCOLS / 4); e += NTHREADS) {
+      const int c = e / (CT_DROWS * (CT_DCOLS / 4)), r = (e / (CT_DCOLS / 4)) % CT_DROWS, q = e % (CT_DCOLS / 4);
+      const int oy = 2 * iy0 + r, ox = 2 * ix0 + 4 * q;
+      const bool ok = oy < a.Hs && ox < a.Ws;
+      const int rem = ok ? a.Ws - ox : 0;  // Ws % 4 == 0 keeps this a multiple of 4; the guard is for safety
+      const float* src = a.dout + (size_t)n * a.dout_ss + ((size_t)(co0 + c) * a.Hs + (ok ? oy : 0)) * a.Ws + (ok ? ox : 0);
+      cp_async16(tma::smem_u32(sd + c * CT_DPS + r * CT_DCOLS + 4 * q), src, rem >= 4 ? 16 : rem * 4);
+    }
+  };
+  // planes of absent channels are zeroed once (their requests are never issued)
+  for (int i = tid; i < 2 * CT_STAGE; i += NTHREADS) stages[i] = 0.f;
+  __syncthreads();
+  if (mine > 0) issue(0);
+  cp_async_commit();
+  float ctot[9][4], c[9][4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ctot[k][q] = 0.f; c[k][q] = 0.f; }
+  for (long long j = 0; j < mine; ++j) {
+    cp_async_wait<0>();
+    __syncthreads();  // stage j landed; stage j^1 is free (everyone finished tile j-1)
+    if (j + 1 < mine) issue(j + 1);
+    cp_async_commit();
+    int n, ix0, iy0;
+    decode(j, n, ix0, iy0);
+    const float* st = stages + (j & 1) * CT_STAGE;
+    const float* sd = st + 16 * CT_XPS;
+    // 32 k-steps of 8 input pixels (row r = ks / 8, columns 8 (ks % 8) ..), 4 per warp
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ks = warp * 4 + u, r = ks >> 3, cx = (ks & 7) * 8;
+      const bool rowok = iy0 + r < a.Hin;
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // q: 0 = (ci g, px t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
+        const int h = q & 1, e = q >> 1;
+        const int px = cx + t + 4 * e;
+        float v = 0.f;
+        if (rowok && ix0 + px < a.Win && g + 8 * h < nci) v = xform_apply(st[(g + 8 * h) * CT_XPS + r * CTC + px], sc[h], sh[h], lo[h]);
+        tf32_split2(v, ah[q], al[q]);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int ky = k / 3, kx = k - 3 * ky;
+        // B (k = px t / t+4, n = co g): dout[co g][2r + ky][2 px + kx]
+        const float* bp = sd + g * CT_DPS + (2 * r + ky) * CT_DCOLS + 2 * (cx + t) + kx;
+        uint32_t bh0, bl0, bh1, bl1;
+        tf32_split2(bp[0], bh0, bl0);
+        tf32_split2(bp[8], bh1, bl1);
+        mma_tf32_16n8k8(c[k], al, bh0, bh1);
+        mma_tf32_16n8k8(c[k], ah, bl0, bl1);
+        mma_tf32_16n8k8(c[k], ah, bh0, bh1);
+      }
+    }
+    if ((j & 1) == 1) {  // flush: the tensor core's truncating accumulation sees chains of 8 k-steps
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ctot[k][q] += c[k][q]; c[k][q] = 0.f; }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // CTA reduction: sred[warp][ci 16][co 8][tap 9]
+  float* sred = stages;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float v0 = ctot[k][0] + c[k][0], v1 = ctot[k][1] + c[k][1], v2 = ctot[k][2] + c[k][2], v3 = ctot[k][3] + c[k][3];
+    sred[warp * 1152 + (g * 8 + 2 * t) * 9 + k] = v0;          // (ci g, co 2t)
+    sred[warp * 1152 + (g * 8 + 2 * t + 1) * 9 + k] = v1;      // (ci g, co 2t+1)
+    sred[warp * 1152 + ((g + 8) * 8 + 2 * t) * 9 + k] = v2;    // (ci g+8, co 2t)
+    sred[warp * 1152 + ((g + 8) * 8 + 2 * t + 1) * 9 + k] = v3;
+  }
+  __syncthreads();
+  for (int i = tid; i < 1152; i += NTHREADS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sred[w * 1152 + i];
+    const int ci = i / 72, co = (i / 9) % 8, k = i % 9;
+    if (ci < nci && co < nco)
+      a.partials[(((size_t)blockIdx.x * a.Cin + ci0 + ci) * a.Cout + co0 + co) * 9 + k] = sum;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -1034,6 +1183,40 @@ int ocrs_det_pw_wgrad_saved(const float* d_a, long long da_ss, const float* y, l
   dim3 grid(ocrs_det_pw_wgrad_saved_workers(N, HW, Cout, Cin), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
   pw_wgrad_saved_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   OCRS_CHECK_LAUNCH("pw_wgrad_saved_kernel");
+  return 0;
+}
+
+// 1 when ocrs_det_convt_wgrad_staged can run on these views (16-byte aligned rows: Win % 4 == 0 and Ws % 4 == 0).
+int ocrs_det_convt_wgrad_staged_ok(const float* x, long long x_ss, int Hin, int Win, const float* dout, long long dout_ss,
+                                   int Hs, int Ws) {
+  return ocrs_plane_tma_ok(x, x_ss, Hin, Win) && ocrs_plane_tma_ok(dout, dout_ss, Hs, Ws) && Win >= 16;
+}
+
+// Rows of the [workers][Cin][Cout][9] partials of ocrs_det_convt_wgrad_staged.
+int ocrs_det_convt_wgrad_staged_workers(int N, int Hin, int Win, int Cin, int Cout) {
+  const int pairs = ocrs_cdiv(Cin, 16) * ocrs_cdiv(Cout, 8);
+  const long long tiles = (long long)N * ocrs_cdiv(Win, CTC) * ocrs_cdiv(Hin, CTR);
+  long long per = (2 * OCRS_NUM_SMS + pairs - 1) / pairs;
+  if (per > tiles) per = tiles;
+  return (int)(per < 1 ? 1 : per);
+}
+
+// ConvTranspose2d(k3, s2) weight gradient, cp.async-staged tiles + mma.sync 3xTF32; same contract as
+// ocrs_det_convt_wgrad (partials in weight layout [Cin][Cout][3][3] per worker, fully written).
+int ocrs_det_convt_wgrad_staged(const float* x, long long x_ss, int N, int Cin, int Hin, int Win, const float* isc,
+                                const float* ish, const float* ilo, const float* dout, long long dout_ss, int Cout,
+                                int Hs, int Ws, float* partials, void* stream) {
+  OCRS_CHECK_ARG(ocrs_det_convt_wgrad_staged_ok(x, x_ss, Hin, Win, dout, dout_ss, Hs, Ws), "convt_wgrad_staged: unaligned views");
+  OCRS_CHECK_ARG(Hs <= 2 * Hin + 1 && Ws <= 2 * Win + 1, "convt_wgrad_staged: crop exceeds the transposed-conv output");
+  ConvtWgArgs a;
+  a.x = x; a.dout = dout; a.x_ss = x_ss; a.dout_ss = dout_ss; a.isc = isc; a.ish = ish; a.ilo = ilo; a.partials = partials;
+  a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.Hs = Hs; a.Ws = Ws; a.N = N;
+  size_t smem = (size_t)2 * CT_STAGE * 4;
+  if (smem < 8 * 1152 * 4) smem = 8 * 1152 * 4;
+  OCRS_CUDA(cudaFuncSetAttribute(convt_wgrad_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ocrs_det_convt_wgrad_staged_workers(N, Hin, Win, Cin, Cout), ocrs_cdiv(Cin, 16) * ocrs_cdiv(Cout, 8));
+  convt_wgrad_staged_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  OCRS_CHECK_LAUNCH("convt_wgrad_staged_kernel");
   return 0;
 }
 

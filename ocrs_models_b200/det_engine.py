@@ -352,10 +352,16 @@ class _DetFunction(torch.autograd.Function):
                 d_up = new_view(N, up_in.C, up_in.H, up_in.W, dev)
                 call("ocrs_det_convt_bwd_data", dlo.p, dlo.ss, N, c, hs[i], ws[i], ptr(t.weight), up_in.C, up_in.H,
                      up_in.W, d_up.p, d_up.ss, st)
-                workers = lib.ocrs_det_convt_wgrad_workers(N, up_in.H, up_in.W)
-                wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
-                call("ocrs_det_convt_wgrad", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
-                     dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
+                if USE_TMA and lib.ocrs_det_convt_wgrad_staged_ok(up_in.p, up_in.ss, up_in.H, up_in.W, dlo.p, dlo.ss, hs[i], ws[i]):
+                    workers = lib.ocrs_det_convt_wgrad_staged_workers(N, up_in.H, up_in.W, up_in.C, c)
+                    wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
+                    call("ocrs_det_convt_wgrad_staged", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
+                         dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
+                else:
+                    workers = lib.ocrs_det_convt_wgrad_workers(N, up_in.H, up_in.W)
+                    wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
+                    call("ocrs_det_convt_wgrad", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
+                         dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
                 dw = torch.empty_like(t.weight)
                 _finalize(wpart, workers, t.weight.numel(), dw, st)
                 brows = lib.ocrs_reduce_rows(N, hs[i] * ws[i])

@@ -221,7 +221,8 @@ def test_pool_fwd_bwd(H, W):
     assert rel_l2(din, a.grad) < 1e-6
 
 
-@pytest.mark.parametrize("N,cin,cout,h,w,Hs,Ws", [(2, 16, 8, 20, 24, 40, 48), (1, 256, 128, 3, 2, 7, 5), (2, 32, 16, 9, 7, 18, 15), (1, 24, 12, 5, 6, 11, 13)])
+@pytest.mark.parametrize("N,cin,cout,h,w,Hs,Ws", [(2, 16, 8, 20, 24, 40, 48), (1, 256, 128, 3, 2, 7, 5), (2, 32, 16, 9, 7, 18, 15), (1, 24, 12, 5, 6, 11, 13),
+                                                  (2, 16, 8, 9, 68, 19, 136), (1, 32, 32, 6, 16, 12, 32), (1, 8, 20, 5, 80, 11, 160)])
 def test_convt_fwd_bwd(N, cin, cout, h, w, Hs, Ws):
     from ocrs_models_b200._lib import call, lib, ptr
 
@@ -257,6 +258,13 @@ def test_convt_fwd_bwd(N, cin, cout, h, w, Hs, Ws):
     dw = torch.empty(cin, cout, 3, 3, device="cuda")
     call("ocrs_finalize_partials", ptr(part), workers, dw.numel(), ptr(dw), _stream())
     assert rel_l2(dw, wt.grad) < 1e-5
+    cs = (cout + 3) * Hs * Ws
+    if lib().ocrs_det_convt_wgrad_staged_ok(ptr(xd), cin * h * w, h, w, ptr(dcat), cs, Hs, Ws):
+        # cp.async-staged version (csrc/det_tma.cu) on TMA-addressable shapes
+        workers = lib().ocrs_det_convt_wgrad_staged_workers(N, h, w, cin, cout)
+        part = torch.full((workers, cin, cout, 3, 3), float("nan"), device="cuda")
+        call("ocrs_det_convt_wgrad_staged", ptr(xd), cin * h * w, N, cin, h, w, *xfd, ptr(dcat), cs, cout, Hs, Ws, ptr(part), _stream())
+        assert rel_l2(part.double().sum(0), wt.grad) < 1e-5, "staged wgrad"
     rows = lib().ocrs_reduce_rows(N, Hs * Ws)
     bp = torch.empty(rows, cout, device="cuda")
     call("ocrs_plane_sum", ptr(dcat), (cout + 3) * Hs * Ws, N, cout, Hs * Ws, ptr(bp), _stream())
