@@ -488,6 +488,7 @@ struct PwWgArgs {
 };
 
 __device__ __forceinline__ void tf32_split2(float v, uint32_t& hi, uint32_t& lo) {
+  // integer add + mask (2 ALU instructions): measured faster than cvt.rna.tf32.f32, which issues on the quarter-rate conversion pipe
   hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
@@ -747,7 +748,18 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
   const long long chunks_per_n = (a.HW + GPX - 1) / GPX;
   const long long total = chunks_per_n * a.N;
   const long long mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  // this thread's cp.async requests of a stage: planes (tid >> 5) + 8 r, 16-byte column (tid & 31)
+  // this thread's cp.async requests of a stage: planes warp + 8 r (r < 6), 16-byte column `lane`. The per-plane parts of
+  // the addresses are computed once; per stage only the (sample, pixel) offset of each tensor changes.
+  const float* pbase[GPLANES / 8];
+  bool pok[GPLANES / 8];
+#pragma unroll
+  for (int r = 0; r < GPLANES / 8; ++r) {
+    const int pl = warp + 8 * r, which = pl >> 4, ch = pl & 15;  // which: 0 = d_a, 1 = y, 2 = dwo
+    pok[r] = ch < (which == 2 ? nci : nco);
+    pbase[r] = which == 0 ? a.d_a + (size_t)(co0 + ch) * a.HW : which == 1 ? a.y + (size_t)(co0 + ch) * a.HW
+                                                                            : a.dwo + (size_t)(ci0 + ch) * a.HW;
+  }
+  const long long dwo_ss = (long long)a.Cin * a.HW;
   auto issue = [&](long long j) {
     const long long w = blockIdx.x + j * gridDim.x;
     const int n = (int)(w / chunks_per_n);
@@ -755,17 +767,11 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
     const long long rem = a.HW - p0;  // pixels left in the plane from this thread's column on
     const int bytes = rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0);
     const long long pc = rem > 0 ? p0 : 0;  // keep the (unread) source address inside the tensor
-    float* st = stages + (j % GSTAGES) * (GPLANES * GPS) + 4 * lane;
+    const long long off[3] = {(long long)n * a.da_ss + pc, (long long)n * a.y_ss + pc, (long long)n * dwo_ss + pc};
+    const uint32_t dst = tma::smem_u32(stages + (j % GSTAGES) * (GPLANES * GPS) + 4 * lane + warp * GPS);
 #pragma unroll
-    for (int r = 0; r < GPLANES / 8; ++r) {
-      const int pl = warp + 8 * r, which = pl >> 4, ch = pl & 15;  // which: 0 = d_a, 1 = y, 2 = dwo
-      const float* src;
-      bool ok;
-      if (which == 0) { src = a.d_a + (size_t)n * a.da_ss + (size_t)(co0 + ch) * a.HW + pc; ok = ch < nco; }
-      else if (which == 1) { src = a.y + (size_t)n * a.y_ss + (size_t)(co0 + ch) * a.HW + pc; ok = ch < nco; }
-      else { src = a.dwo + ((size_t)n * a.Cin + ci0 + ch) * a.HW + pc; ok = ch < nci; }
-      if (ok) cp_async16(tma::smem_u32(st + pl * GPS), src, bytes);  // bytes < 16 zero-fills the tail of a plane
-    }
+    for (int r = 0; r < GPLANES / 8; ++r)
+      if (pok[r]) cp_async16(dst + r * 8 * GPS * 4, pbase[r] + off[r >> 1], bytes);  // bytes < 16 zero-fills a plane's tail
   };
   // planes of channels this CTA does not have (8-channel blocks, Cin = 1) are zeroed once and never requested
   for (int i = tid; i < GSTAGES * GPLANES * GPS; i += NTHREADS) {
