@@ -91,8 +91,6 @@ SIGNATURES: dict[str, list] = {
     "ocrs_rec_bn_act_pool_bwd_reduce": [P, I, I, I, I, I, I, I, I, P, P, P, P, P, L, L, L, P, P],
     "ocrs_rec_bn_act_pool_bwd_apply": [P, I, I, I, I, I, I, I, I, P, P, P, P, P, P, L, L, L, P, P],
     "ocrs_relu_bwd": [P, P, L, P],
-    "ocrs_gru_layer_fwd": [P, P, P, P, P, P, P, P, I, I, P],
-    "ocrs_gru_layer_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_gru_layer_fwd_persist": [P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_gru_layer_bwd_persist": [P, P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_log_softmax_fwd": [P, P, I, I, P],

@@ -89,7 +89,9 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, 
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * CTC_WARPS + (threadIdx.x >> 5);
   if (n >= N) return;
-  const int S = max(tgt_len[n], 0);
+  // lengths and labels come from the caller's tensors: clamp them into what the shared-memory frame and the lane
+  // layout can address (torch raises on such inputs; here they must at least never index out of bounds)
+  const int S = min(max(tgt_len[n], 0), min(tgt_stride, 32 * NP - 1));
   const int Tn = min(in_len[n], T);
   const int* tg = targets + (size_t)n * tgt_stride;
   if (Tn <= 0) {
@@ -102,10 +104,10 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int* __restrict__ targets, 
   for (int p = 0; p < NP; ++p) {
     const int i = lane * NP + p;
     const bool vl = i < S, vb = i <= S;
-    const int l = vl ? tg[i] : blank;
+    const int l = vl ? min(max(tg[i], 0), C - 1) : blank;
     P.lab[p] = l;
     P.vl[p] = vl;
-    skip[p] = vl && i >= 1 && tg[i - 1] != l;
+    skip[p] = vl && i >= 1 && min(max(tg[i - 1], 0), C - 1) != l;
     P.sc_b[p] = vb ? LOG2E : 0.f; P.of_b[p] = vb ? 0.f : NEG;
     P.sc_l[p] = vl ? LOG2E : 0.f; P.of_l[p] = vl ? 0.f : NEG;
   }
@@ -199,7 +201,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
   // so the gradient is bitwise deterministic
   int* occ = reinterpret_cast<int*>(ctc_smem + (size_t)wid * (NCH * 32 + DB * SLOT));
   float* ring = reinterpret_cast<float*>(occ + NCH * 32);
-  const int S = max(tgt_len[n], 0);
+  const int S = min(max(tgt_len[n], 0), min(tgt_stride, 32 * NP - 1));
   const int Tn = min(in_len[n], T);
   const int* tg = targets + (size_t)n * tgt_stride;
   const size_t tstride = (size_t)N * C;
@@ -230,10 +232,10 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int* __restrict__ targe
   for (int p = 0; p < NP; ++p) {
     const int i = lane * NP + p;
     const bool vl = i < S, vb = i <= S;
-    const int l = vl ? tg[i] : blank;
+    const int l = vl ? min(max(tg[i], 0), C - 1) : blank;
     P.lab[p] = l;
     P.vl[p] = vl;
-    skip[p] = vl && (i + 1 < S) && tg[i + 1] != l;
+    skip[p] = vl && (i + 1 < S) && min(max(tg[i + 1], 0), C - 1) != l;
     P.sc_b[p] = vb ? LOG2E : 0.f; P.of_b[p] = vb ? 0.f : NEG;
     P.sc_l[p] = vl ? LOG2E : 0.f; P.of_l[p] = vl ? 0.f : NEG;
   }

@@ -6,9 +6,9 @@
 //   3. pwT_bwd            : g[ci]   = sum_co Wpw[co][ci] * dy[co]
 //   4. pw_wgrad           : dWpw[co][ci] = sum_p dy[co][p] * dwout[ci][p]   (dwout recomputed)
 //   5. dw_bwd             : d_xact = dw3x3^T(g),  dWdw[ci][k] = sum_p g[ci][p] * xact[ci][p+k]
-// Weight-gradient reductions over pixels are "skinny GEMMs" (M,N <= 16 per block, K = pixels):
-// operands are staged per 256-pixel tile in shared memory and each thread owns a 4x4 output
-// patch; per-block partial results are reduced in double by finalize_partials (deterministic).
+// Weight-gradient reductions over pixels are "skinny GEMMs" (M,N <= 16 per block, K = pixels) on warp-level
+// mma.sync 3xTF32; per-block partial results are reduced in double by finalize_partials (deterministic).
+// These kernels serve the shapes TMA cannot address (W % 4 != 0); csrc/det_tma.cu holds the main path.
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -251,150 +251,8 @@ pwT_bwd_kernel(const float* __restrict__ d_a, long long da_ss, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Skinny GEMM core: sa/sb hold 256 pixels x 16 rows (row stride SG_LD floats). Thread t owns the
-// 4x4 patch (rows a: 4*((t&15)>>2).., rows b: 4*(t&3)..) over pixel slice t>>4 (16 pixels).
-constexpr int SG_LD = 20;
-__device__ __forceinline__ void skinny_accumulate(const float* sa, const float* sb, float acc[4][4]) {
-  const int t = threadIdx.x, slice = t >> 4, ab = (t & 15) >> 2, bb = t & 3;
-#pragma unroll 4
-  for (int pp = 0; pp < 16; ++pp) {
-    const int p = slice * 16 + pp;
-    const float4 a = *reinterpret_cast<const float4*>(sa + p * SG_LD + ab * 4);
-    const float4 b = *reinterpret_cast<const float4*>(sb + p * SG_LD + bb * 4);
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-  }
-}
-// Reduce the 16 pixel slices; thread t < 256 returns element (row a = t>>4, row b = t&15).
-__device__ __forceinline__ float skinny_reduce(float* scratch /* >= 16*256 floats */, float acc[4][4]) {
-  const int t = threadIdx.x, slice = t >> 4, ab = (t & 15) >> 2, bb = t & 3;
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) scratch[slice * 256 + (ab * 4 + i) * 16 + bb * 4 + j] = acc[i][j];
-  __syncthreads();
-  float s = 0.f;
-#pragma unroll
-  for (int sl = 0; sl < 16; ++sl) s += scratch[sl * 256 + t];
-  return s;
-}
-
-// dWpw[co][ci] = sum_p dy[co][p] * dwout[ci][p], dwout = dw3x3(xform(x)) recomputed per tile.
-// grid = (workers, co_tiles * ci_tiles); tile = 32x8 pixels of one image.
+// dWpw[co][ci] = sum_p dy[co][p] * dwout[ci][p], dwout = dw3x3(xform(x)) recomputed per tile of 32x8 pixels.
 constexpr int WG_TW = 32, WG_TH = 8, WG_SROW = WG_TW + 2, WG_SPLANE = (WG_TH + 2) * WG_SROW;
-constexpr int WG_SMEM_FLOATS = 16 * WG_SPLANE + 2 * 256 * SG_LD;
-__global__ void __launch_bounds__(256)
-pw_wgrad_kernel(const float* __restrict__ d_a, long long da_ss, const float* __restrict__ y,
-                long long y_ss, int Cout, DyCoef k, const float* __restrict__ x, long long x_ss,
-                int Cin, int H, int W, const float* __restrict__ isc, const float* __restrict__ ish,
-                const float* __restrict__ ilo, const float* __restrict__ wdw, int N, int tiles_x,
-                int tiles_y, float* __restrict__ partials) {
-  extern __shared__ __align__(16) float smem[];
-  float* xs = smem;                      // [16][WG_SPLANE]
-  float* sa = smem + 16 * WG_SPLANE;     // dy    [256][SG_LD]
-  float* sb = sa + 256 * SG_LD;          // dwout [256][SG_LD]
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int cit = (Cin + 15) / 16;
-  const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
-  const int nco = min(16, Cout - co0), nci = min(16, Cin - ci0);
-  const size_t HW = (size_t)H * W;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  __shared__ float skc[6][16];
-  __shared__ float swd[16][9];
-  __shared__ float sxf[3][16];
-  if (tid >= 32 && tid < 48 && isc) {
-    const int c = tid - 32;
-    const bool v = c < nci;
-    sxf[0][c] = v ? isc[ci0 + c] : 1.f; sxf[1][c] = v ? ish[ci0 + c] : 0.f; sxf[2][c] = v ? ilo[ci0 + c] : -INFINITY;
-  }
-  if (tid < 16) {
-    const bool v = tid < nco;
-    skc[0][tid] = v ? k.sc[co0 + tid] : 0.f; skc[1][tid] = v ? k.sh[co0 + tid] : 0.f;
-    skc[2][tid] = v ? k.lo[co0 + tid] : 0.f; skc[3][tid] = v ? k.k1[co0 + tid] : 0.f;
-    skc[4][tid] = v ? k.k2[co0 + tid] : 0.f; skc[5][tid] = v ? k.k3[co0 + tid] : 0.f;
-  }
-  if (tid < 144) swd[tid / 9][tid % 9] = (tid / 9 < nci) ? wdw[(size_t)(ci0 + tid / 9) * 9 + tid % 9] : 0.f;
-  const int tiles = tiles_x * tiles_y;
-  const long long total = (long long)N * tiles;
-  for (long long work = blockIdx.x; work < total; work += gridDim.x) {
-    const int n = (int)(work / tiles), tile = (int)(work % tiles);
-    const int x0 = (tile % tiles_x) * WG_TW, y0 = (tile / tiles_x) * WG_TH;
-    __syncthreads();
-    {
-      constexpr int NSLOT = (WG_SPLANE + 255) / 256;
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        const int pos = tid + 256 * sl;
-        if (pos < WG_SPLANE) {
-          const int ry = pos / WG_SROW, rx = pos - ry * WG_SROW;
-          const int gy = y0 + ry - 1, gx = x0 + rx - 1;
-          const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-          const float* src = x + (size_t)n * x_ss + (size_t)ci0 * HW + (size_t)(in ? gy * W + gx : 0);
-          float v[16];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = (in && c < nci) ? src[(size_t)c * HW] : 0.f;
-          if (isc && in) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) if (c < nci) v[c] = xform_apply(v[c], sxf[0][c], sxf[1][c], sxf[2][c]);
-          }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) xs[c * WG_SPLANE + pos] = v[c];
-        }
-      }
-    }
-    // dy for this thread's pixel
-    const int gy = y0 + ty, gx = x0 + tx;
-    const bool ok = gy < H && gx < W;
-    float va[16];
-#pragma unroll
-    for (int o = 0; o < 16; ++o) {
-      float v = 0.f;
-      if (ok && o < nco) {
-        const size_t off = (size_t)(co0 + o) * HW + (size_t)gy * W + gx;
-        v = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], skc[0][o], skc[1][o], skc[2][o],
-                  skc[3][o], skc[4][o], skc[5][o]);
-      }
-      va[o] = v;
-    }
-#pragma unroll
-    for (int o4 = 0; o4 < 4; ++o4)
-      *reinterpret_cast<float4*>(sa + tid * SG_LD + o4 * 4) =
-          make_float4(va[o4 * 4], va[o4 * 4 + 1], va[o4 * 4 + 2], va[o4 * 4 + 3]);
-    __syncthreads();
-    float vb[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float s = 0.f;
-      if (ok && c < nci) {
-        const float* t = xs + c * WG_SPLANE + ty * WG_SROW + tx;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) s = fmaf(t[ky * WG_SROW + kx], swd[c][ky * 3 + kx], s);
-      }
-      vb[c] = s;
-    }
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4)
-      *reinterpret_cast<float4*>(sb + tid * SG_LD + c4 * 4) =
-          make_float4(vb[c4 * 4], vb[c4 * 4 + 1], vb[c4 * 4 + 2], vb[c4 * 4 + 3]);
-    __syncthreads();
-    skinny_accumulate(sa, sb, acc);
-  }
-  const float s = skinny_reduce(smem, acc);
-  const int o = tid >> 4, c = tid & 15;
-  // partial layout: [worker][Cout][Cin]
-  if (o < nco && c < nci)
-    partials[((size_t)blockIdx.x * Cout + co0 + o) * Cin + ci0 + c] = s;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core version of pw_wgrad. The reduction dW[co][ci] = sum_p dy[co][p] * dwout[ci][p] has
@@ -879,68 +737,6 @@ convt_bwd_data_kernel(const float* __restrict__ dout, long long dout_ss, int Cou
 }
 
 // ConvTranspose2d weight gradient: dW[ci][co][k] = sum_p xact[ci][p] * d_out[co][2iy+ky][2ix+kx].
-// Rows a = 16 input channels, rows b = 16 of the Cout*9 (co, tap) pairs. grid = (workers, tiles).
-__global__ void __launch_bounds__(256)
-convt_wgrad_kernel(const float* __restrict__ x, long long x_ss, int Cin, int Hin, int Win,
-                   const float* __restrict__ isc, const float* __restrict__ ish,
-                   const float* __restrict__ ilo, const float* __restrict__ dout,
-                   long long dout_ss, int Cout, int Hs, int Ws, int N, float* __restrict__ partials) {
-  __shared__ __align__(16) float smem[2 * 256 * SG_LD];
-  float* sa = smem;
-  float* sb = smem + 256 * SG_LD;
-  const int tid = threadIdx.x;
-  const int CK = Cout * 9;
-  const int bt = (CK + 15) / 16;
-  const int ci0 = (blockIdx.y / bt) * 16, b0 = (blockIdx.y % bt) * 16;
-  const int nci = min(16, Cin - ci0), nb = min(16, CK - b0);
-  const size_t HWi = (size_t)Hin * Win, HWs = (size_t)Hs * Ws;
-  const long long total = (long long)N * HWi;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long base = (long long)blockIdx.x * 256; base < total; base += (long long)gridDim.x * 256) {
-    const long long pidx = base + tid;
-    const bool ok = pidx < total;
-    const int n = ok ? (int)(pidx / HWi) : 0;
-    const int rem = ok ? (int)(pidx % HWi) : 0;
-    const int iy = rem / Win, ix = rem - iy * Win;
-    float va[16], vb[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float v = 0.f;
-      if (ok && c < nci) {
-        v = x[(size_t)n * x_ss + (size_t)(ci0 + c) * HWi + rem];
-        if (isc) v = xform_apply(v, isc[ci0 + c], ish[ci0 + c], ilo[ci0 + c]);
-      }
-      va[c] = v;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float v = 0.f;
-      if (ok && j < nb) {
-        const int co = (b0 + j) / 9, kk = (b0 + j) - co * 9, ky = kk / 3, kx = kk - ky * 3;
-        const int oy = 2 * iy + ky, ox = 2 * ix + kx;
-        if (oy < Hs && ox < Ws) v = dout[(size_t)n * dout_ss + (size_t)co * HWs + (size_t)oy * Ws + ox];
-      }
-      vb[j] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      *reinterpret_cast<float4*>(sa + tid * SG_LD + q * 4) = make_float4(va[q * 4], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
-      *reinterpret_cast<float4*>(sb + tid * SG_LD + q * 4) = make_float4(vb[q * 4], vb[q * 4 + 1], vb[q * 4 + 2], vb[q * 4 + 3]);
-    }
-    __syncthreads();
-    skinny_accumulate(sa, sb, acc);
-  }
-  const float s = skinny_reduce(smem, acc);
-  const int c = tid >> 4, j = tid & 15;
-  // partial layout [worker][Cin][Cout*9] == weight layout [Cin][Cout][3][3]
-  if (c < nci && j < nb) partials[((size_t)blockIdx.x * Cin + ci0 + c) * CK + b0 + j] = s;
-}
-
 // Tensor-core version (same fragment trick as pw_wgrad_mma_kernel): rows a = 16 input channels,
 // columns b = 16 of the Cout*9 (co, tap) pairs, K = input pixels; operands gathered from global
 // memory directly in mma.sync fragment layout, 3xTF32, accumulators flushed every 4 k-steps.
@@ -1146,20 +942,10 @@ int ocrs_det_pw_wgrad(const float* d_a, long long da_ss, const float* y, long lo
                       const float* k1, const float* k2, const float* k3, const float* x,
                       long long x_ss, int Cin, const float* isc, const float* ish, const float* ilo,
                       const float* wdw, float* partials, void* stream) {
-  static bool attr_set = false;
-  const size_t smem = WG_SMEM_FLOATS * sizeof(float);
-  if (!attr_set) {
-    OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   DyCoef k{sc, sh, lo, k1, k2, k3};
   const int tiles_x = ocrs_cdiv(W, WG_TW), tiles_y = ocrs_cdiv(H, WG_TH);
   dim3 grid(ocrs_det_pw_wgrad_workers(N, H, W), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
-  if (getenv("OCRS_PW_WGRAD_SIMT"))
-    pw_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin, H, W, isc,
-                                                              ish, ilo, wdw, N, tiles_x, tiles_y, partials);
-  else
-    pw_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin, H, W, isc,
+  pw_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, k, x, x_ss, Cin, H, W, isc,
                                                                ish, ilo, wdw, N, tiles_x, tiles_y, partials);
   OCRS_CHECK_LAUNCH("pw_wgrad_kernel");
   return 0;
@@ -1253,11 +1039,7 @@ int ocrs_det_convt_wgrad(const float* x, long long x_ss, int N, int Cin, int Hin
                          const float* isc, const float* ish, const float* ilo, const float* dout,
                          long long dout_ss, int Cout, int Hs, int Ws, float* partials, void* stream) {
   dim3 grid(ocrs_det_convt_wgrad_workers(N, Hin, Win), ocrs_cdiv(Cin, 16) * ocrs_cdiv(Cout * 9, 16));
-  if (getenv("OCRS_CONVT_WGRAD_SIMT"))
-    convt_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout, dout_ss,
-                                                               Cout, Hs, Ws, N, partials);
-  else
-    convt_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout,
+  convt_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, Cin, Hin, Win, isc, ish, ilo, dout,
                                                                    dout_ss, Cout, Hs, Ws, N, partials);
   OCRS_CHECK_LAUNCH("convt_wgrad_kernel");
   return 0;

@@ -15,7 +15,7 @@
 namespace {
 
 // state words (int32)
-enum { ST_NPOS = 0, ST_NNEG = 1, ST_K = 2, ST_PREFIX = 4, ST_KREM = 6, ST_NEQ = 8, ST_WORDS = 16 };
+enum { ST_NPOS = 0, ST_NNEG = 1, ST_K = 2, ST_NAN = 3, ST_PREFIX = 4, ST_KREM = 6, ST_NEQ = 8, ST_WORDS = 16 };
 constexpr int NBINS = 2048;
 
 __device__ __forceinline__ int key_bin(unsigned key, int pass) {
@@ -32,8 +32,10 @@ bce_map_kernel(const float* __restrict__ p, const float* __restrict__ t, long lo
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
   __syncthreads();
   int np = 0, nn = 0;
+  bool bad = false;  // a NaN prediction or target must surface as a NaN loss (the reference raises / propagates)
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float tv = t[i], pv = p[i];
+    bad |= (pv != pv) || (tv != tv);
     const float tc = fminf(fmaxf(tv, 0.f), 1.f);
     const float lp = fmaxf(logf(pv), -100.f), l1 = fmaxf(logf(1.f - pv), -100.f);
     const float L = fabsf(-(tc * lp + (1.f - tc) * l1));
@@ -47,6 +49,7 @@ bce_map_kernel(const float* __restrict__ p, const float* __restrict__ t, long lo
   if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt[0], np); atomicAdd(&cnt[1], nn); }
   __syncthreads();
   if (threadIdx.x == 0) { atomicAdd(&st[ST_NPOS], cnt[0]); atomicAdd(&st[ST_NNEG], cnt[1]); }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&st[ST_NAN], 1);
 }
 
 __global__ void select_init_kernel(int* st, unsigned* hist) {
@@ -132,7 +135,7 @@ __global__ void bce_loss_finalize_kernel(const float* __restrict__ partials, int
   const int k = st[ST_K];
   for (int c = 0; c < 2; ++c)
     s += (double)st[ST_KREM + c] * (double)__uint_as_float((unsigned)st[ST_PREFIX + c]);
-  loss[0] = k > 0 ? (float)(s / (2.0 * k)) : __int_as_float(0x7fc00000);
+  loss[0] = (k > 0 && st[ST_NAN] == 0) ? (float)(s / (2.0 * k)) : __int_as_float(0x7fc00000);
 }
 
 // d loss / d p (aten binary_cross_entropy_backward: (p - t) / max(p (1 - p), 1e-12)).

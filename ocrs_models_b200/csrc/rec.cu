@@ -484,124 +484,6 @@ __global__ void relu_bwd_kernel(const float* __restrict__ a, float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// GRU (nn.GRU gate order r, z, n; hidden 256; both directions in one launch via blockIdx.y).
-constexpr int GH = 256;
-struct GruDirs {
-  const float* gi[2];    // [T*N][768] input projections (incl. b_ih)
-  const float* whh[2];   // fwd: [768][256]; bwd step: transposed [256][768]
-  const float* bhh[2];   // [768]
-};
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-// One time step. out: [T][N][512] (dir d in columns d*256..); gates: [T][N][2][4][256] (r,z,n,gh_n).
-// Thread = (2 batch rows, 1 hidden unit); block = 32 row-pairs x 4 units.
-__global__ void __launch_bounds__(128)
-gru_step_fwd_kernel(GruDirs p, float* __restrict__ out, float* __restrict__ gates, int T, int N, int step) {
-  const int d = blockIdx.y;
-  const int t = d == 0 ? step : T - 1 - step;
-  const int tp = d == 0 ? t - 1 : t + 1;
-  const int j = blockIdx.x * 4 + (threadIdx.x & 3);
-  const int n0 = (blockIdx.z * 32 + (threadIdx.x >> 2)) * 2;
-  if (n0 >= N) return;
-  const bool two = n0 + 1 < N;
-  const int n1 = two ? n0 + 1 : n0;
-  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  const float* w = p.whh[d];
-  float hp0 = 0.f, hp1 = 0.f;
-  if (step > 0) {
-    const float* h0 = out + ((size_t)tp * N + n0) * 512 + d * GH;
-    const float* h1 = out + ((size_t)tp * N + n1) * 512 + d * GH;
-    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)j * GH);
-    const float4* wz = reinterpret_cast<const float4*>(w + (size_t)(GH + j) * GH);
-    const float4* wn = reinterpret_cast<const float4*>(w + (size_t)(2 * GH + j) * GH);
-#pragma unroll 4
-    for (int k4 = 0; k4 < GH / 4; ++k4) {
-      const float4 a = reinterpret_cast<const float4*>(h0)[k4], b = reinterpret_cast<const float4*>(h1)[k4];
-      const float4 r4 = __ldg(wr + k4), z4 = __ldg(wz + k4), q4 = __ldg(wn + k4);
-      acc[0][0] = fmaf(a.x, r4.x, fmaf(a.y, r4.y, fmaf(a.z, r4.z, fmaf(a.w, r4.w, acc[0][0]))));
-      acc[0][1] = fmaf(a.x, z4.x, fmaf(a.y, z4.y, fmaf(a.z, z4.z, fmaf(a.w, z4.w, acc[0][1]))));
-      acc[0][2] = fmaf(a.x, q4.x, fmaf(a.y, q4.y, fmaf(a.z, q4.z, fmaf(a.w, q4.w, acc[0][2]))));
-      acc[1][0] = fmaf(b.x, r4.x, fmaf(b.y, r4.y, fmaf(b.z, r4.z, fmaf(b.w, r4.w, acc[1][0]))));
-      acc[1][1] = fmaf(b.x, z4.x, fmaf(b.y, z4.y, fmaf(b.z, z4.z, fmaf(b.w, z4.w, acc[1][1]))));
-      acc[1][2] = fmaf(b.x, q4.x, fmaf(b.y, q4.y, fmaf(b.z, q4.z, fmaf(b.w, q4.w, acc[1][2]))));
-    }
-    hp0 = h0[j];
-    hp1 = h1[j];
-  }
-  const float br = p.bhh[d][j], bz = p.bhh[d][GH + j], bn = p.bhh[d][2 * GH + j];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    if (q == 1 && !two) break;
-    const int n = q == 0 ? n0 : n1;
-    const float* gi = p.gi[d] + ((size_t)t * N + n) * 768;
-    const float r = sigmoidf_(gi[j] + acc[q][0] + br);
-    const float z = sigmoidf_(gi[GH + j] + acc[q][1] + bz);
-    const float ghn = acc[q][2] + bn;
-    const float nn = tanhf(gi[2 * GH + j] + r * ghn);
-    const float hp = q == 0 ? hp0 : hp1;
-    const float h = (1.f - z) * nn + z * hp;
-    out[((size_t)t * N + n) * 512 + d * GH + j] = h;
-    float* gs = gates + (((size_t)t * N + n) * 2 + d) * 4 * GH;
-    gs[j] = r; gs[GH + j] = z; gs[2 * GH + j] = nn; gs[3 * GH + j] = ghn;
-  }
-}
-
-// One BPTT step. dout: [T][N][512]; dgi/dgh: per direction [T*N][768]; carry: [2][N][256] holds
-// dh(t_next) * z(t_next). whh here is the TRANSPOSED recurrent weight [256][768].
-struct GruBwd {
-  const float* whhT[2];
-  float* dgi[2];
-  float* dgh[2];
-};
-__global__ void __launch_bounds__(128)
-gru_step_bwd_kernel(GruBwd p, const float* __restrict__ dout, const float* __restrict__ out,
-                    const float* __restrict__ gates, float* __restrict__ carry, int T, int N, int step) {
-  const int d = blockIdx.y;
-  // backward visits time in the reverse of the forward order of this direction
-  const int t = d == 0 ? T - 1 - step : step;
-  const int tnext = d == 0 ? t + 1 : t - 1;  // the step processed just before (later in forward order)
-  const int tprev = d == 0 ? t - 1 : t + 1;  // source of h_prev in forward order
-  const int k = blockIdx.x * 4 + (threadIdx.x & 3);
-  const int n0 = (blockIdx.z * 32 + (threadIdx.x >> 2)) * 2;
-  if (n0 >= N) return;
-  const bool two = n0 + 1 < N;
-  const int n1 = two ? n0 + 1 : n0;
-  float acc[2] = {0.f, 0.f};
-  if (step > 0) {
-    const float4* g0 = reinterpret_cast<const float4*>(p.dgh[d] + ((size_t)tnext * N + n0) * 768);
-    const float4* g1 = reinterpret_cast<const float4*>(p.dgh[d] + ((size_t)tnext * N + n1) * 768);
-    const float4* w = reinterpret_cast<const float4*>(p.whhT[d] + (size_t)k * 768);
-#pragma unroll 4
-    for (int j4 = 0; j4 < 768 / 4; ++j4) {
-      const float4 a = g0[j4], b = g1[j4], w4 = __ldg(w + j4);
-      acc[0] = fmaf(a.x, w4.x, fmaf(a.y, w4.y, fmaf(a.z, w4.z, fmaf(a.w, w4.w, acc[0]))));
-      acc[1] = fmaf(b.x, w4.x, fmaf(b.y, w4.y, fmaf(b.z, w4.z, fmaf(b.w, w4.w, acc[1]))));
-    }
-  }
-  const bool has_prev = tprev >= 0 && tprev < T;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    if (q == 1 && !two) break;
-    const int n = q == 0 ? n0 : n1;
-    float* cr = carry + ((size_t)d * N + n) * GH + k;
-    float dh = dout[((size_t)t * N + n) * 512 + d * GH + k] + acc[q];
-    if (step > 0) dh += *cr;
-    const float* gs = gates + (((size_t)t * N + n) * 2 + d) * 4 * GH;
-    const float r = gs[k], z = gs[GH + k], nn = gs[2 * GH + k], ghn = gs[3 * GH + k];
-    const float hp = has_prev ? out[((size_t)tprev * N + n) * 512 + d * GH + k] : 0.f;
-    const float dn = dh * (1.f - z) * (1.f - nn * nn);
-    const float dz = dh * (hp - nn) * z * (1.f - z);
-    const float dr = dn * ghn * r * (1.f - r);
-    float* gi = p.dgi[d] + ((size_t)t * N + n) * 768;
-    float* gh = p.dgh[d] + ((size_t)t * N + n) * 768;
-    gi[k] = dr; gi[GH + k] = dz; gi[2 * GH + k] = dn;
-    gh[k] = dr; gh[GH + k] = dz; gh[2 * GH + k] = dn * r;
-    *cr = dh * z;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // LogSoftmax over the last dim, one warp per row (models.py:250), and its backward.
 __global__ void log_softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -729,31 +611,6 @@ int ocrs_relu_bwd(const float* act, float* grad, long long n, void* stream) {
   OCRS_CHECK_ARG(n % 4 == 0, "relu_bwd: length must be a multiple of 4");
   relu_bwd_kernel<<<ocrs_cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(act, grad, n / 4);
   OCRS_CHECK_LAUNCH("relu_bwd_kernel");
-  return 0;
-}
-
-// Runs all T steps of one bidirectional GRU layer. gi_f/gi_r: [T*N][768]; whh_*: [768][256].
-int ocrs_gru_layer_fwd(const float* gi_f, const float* gi_r, const float* whh_f, const float* whh_r,
-                       const float* bhh_f, const float* bhh_r, float* out, float* gates, int T, int N,
-                       void* stream) {
-  OCRS_CHECK_ARG(T > 0 && N > 0, "gru_layer_fwd: bad dims");
-  GruDirs p{{gi_f, gi_r}, {whh_f, whh_r}, {bhh_f, bhh_r}};
-  dim3 grid(GH / 4, 2, ocrs_cdiv(N, 64));
-  for (int s = 0; s < T; ++s)
-    gru_step_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, out, gates, T, N, s);
-  OCRS_CHECK_LAUNCH_N("gru_step_fwd_kernel", T);
-  return 0;
-}
-
-// whhT_*: transposed recurrent weights [256][768]; carry: [2][N][256] scratch.
-int ocrs_gru_layer_bwd(const float* whhT_f, const float* whhT_r, const float* dout, const float* out,
-                       const float* gates, float* dgi_f, float* dgi_r, float* dgh_f, float* dgh_r,
-                       float* carry, int T, int N, void* stream) {
-  GruBwd p{{whhT_f, whhT_r}, {dgi_f, dgi_r}, {dgh_f, dgh_r}};
-  dim3 grid(GH / 4, 2, ocrs_cdiv(N, 64));
-  for (int s = 0; s < T; ++s)
-    gru_step_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, dout, out, gates, carry, T, N, s);
-  OCRS_CHECK_LAUNCH_N("gru_step_bwd_kernel", T);
   return 0;
 }
 

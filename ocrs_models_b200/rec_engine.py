@@ -21,9 +21,6 @@ TARGET_BLOCKS = 2 * 148
 # "tc": tcgen05 3xTF32 tensor-core GEMM (csrc/gemm_tc.cu) wherever TMA alignment allows, else the
 # fp32 CUDA-core GEMM (csrc/gemm.cu). OCRS_GEMM=simt forces the latter (A/B testing).
 GEMM_BACKEND = os.environ.get("OCRS_GEMM", "tc")
-# "persist": one cluster-persistent launch per GRU layer and direction pair (csrc/gru_persist.cu);
-# "steps": one launch per time step (csrc/rec.cu), kept for A/B testing.
-GRU_BACKEND = os.environ.get("OCRS_GRU", "persist")
 # OCRS_EXACT_FWD=1 runs the forward convolutions on the fp32-FMA GEMM instead of the tensor cores.
 EXACT_FWD = os.environ.get("OCRS_EXACT_FWD", "0") == "1"
 # Implicit-GEMM 3x3 convolutions (im2col folded into the TMA coordinates); OCRS_IMPLICIT=0 goes back to
@@ -282,8 +279,7 @@ class _RecFunction(torch.autograd.Function):
                     gi.append(gemm(layer_in, isz, True, w_ih, isz, True, TN, 768, isz, st, bias=b_ih, b_weight=True))
                 out = _empty((T, N, 512), dev)
                 gates = _empty((T, N, 2, 4, 256), dev)
-                call("ocrs_gru_layer_fwd_persist" if GRU_BACKEND == "persist" else "ocrs_gru_layer_fwd",
-                     ptr(gi[0]), ptr(gi[1]), ptr(getattr(gru, f"weight_hh_l{layer}")),
+                call("ocrs_gru_layer_fwd_persist", ptr(gi[0]), ptr(gi[1]), ptr(getattr(gru, f"weight_hh_l{layer}")),
                      ptr(getattr(gru, f"weight_hh_l{layer}_reverse")), ptr(getattr(gru, f"bias_hh_l{layer}")),
                      ptr(getattr(gru, f"bias_hh_l{layer}_reverse")), ptr(out), ptr(gates), T, N, st)
                 gru_rec.append(dict(x=layer_in, out=out, gates=gates, isz=isz))
@@ -330,13 +326,8 @@ class _RecFunction(torch.autograd.Function):
                     whhT.append(t_)
                 dgi = [_empty((TN, 768), dev) for _ in range(2)]
                 dgh = [_empty((TN, 768), dev) for _ in range(2)]
-                if GRU_BACKEND == "persist":
-                    call("ocrs_gru_layer_bwd_persist", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates),
-                         ptr(dgi[0]), ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), T, N, st)
-                else:
-                    carry = _empty((2, N, 256), dev)
-                    call("ocrs_gru_layer_bwd", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates),
-                         ptr(dgi[0]), ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), ptr(carry), T, N, st)
+                call("ocrs_gru_layer_bwd_persist", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates),
+                     ptr(dgi[0]), ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), T, N, st)
                 d_in = _empty((TN, isz), dev)
                 for d, nm in enumerate(names):
                     w_ih = getattr(gru, "weight_ih_" + nm)

@@ -113,3 +113,17 @@ def test_large_batch_property():
     lr, gr = _run_oracle(lp.detach()[:, idx].cpu(), tgt[idx].cpu(), torch.full((8,), 200), torch.full((8,), S), "sum")
     ours = lp.grad[:, idx].cpu() * (N * S)
     assert (ours - gr).abs().max().item() < 2e-3  # O(1) posteriors, fp32 lattice drift (see test_vs_oracle)
+
+
+def test_out_of_range_labels_and_lengths_do_not_fault():
+    """Labels outside [0, C) and target lengths beyond the padded width are clamped inside the kernels:
+    the call must complete without an out-of-bounds access and give finite-or-inf values, never a sticky CUDA error."""
+    from ocrs_models_b200 import CTCLoss
+
+    g = torch.Generator().manual_seed(0)
+    lp = torch.log_softmax(torch.randn(20, 3, 7, generator=g), 2).cuda().requires_grad_(True)
+    tg = torch.tensor([[1, 99, -4, 2], [3, 3, 3, 3], [6, 5, 4, 3]], dtype=torch.int32).cuda()
+    loss = CTCLoss(reduction="sum", zero_infinity=True)(lp, tg, torch.tensor([20, 20, 20]), torch.tensor([4, 9, 2]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss) and torch.isfinite(lp.grad).all()

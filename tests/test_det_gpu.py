@@ -315,6 +315,16 @@ def test_balanced_bce_saturated_and_ties():
     assert abs(go.sum() - gr.sum()) < 1e-4 * gr.abs().sum()
 
 
+def test_balanced_bce_nan_prediction_gives_nan_loss():
+    from ocrs_models_b200 import balanced_cross_entropy_loss
+
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(1, 1, 16, 16, generator=g) * 0.8 + 0.1
+    p[0, 0, 3, 3] = float("nan")
+    t = (torch.rand(1, 1, 16, 16, generator=g) < 0.3).float()
+    assert torch.isnan(balanced_cross_entropy_loss(p.cuda(), t.cuda()))  # a diverged run must not look healthy
+
+
 def test_balanced_bce_degenerate_no_positives():
     from ocrs_models_b200 import balanced_cross_entropy_loss
 

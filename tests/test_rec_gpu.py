@@ -156,8 +156,7 @@ def test_conv0_fwd_bwd():
 
 
 @pytest.mark.parametrize("T,N", [(9, 3), (25, 64), (6, 70)])
-@pytest.mark.parametrize("backend", ["persist", "steps"])
-def test_gru_layer_fwd_bwd(T, N, backend):
+def test_gru_layer_fwd_bwd(T, N):
     from ocrs_models_b200._lib import call, ptr
     from ocrs_models_b200.rec_engine import gemm
 
@@ -183,20 +182,15 @@ def test_gru_layer_fwd_bwd(T, N, backend):
     gi = [gemm(xd, I, True, D["w_ih" + s], I, True, T * N, 768, I, st, bias=D["b_ih" + s]) for s in ("", "_reverse")]
     out = torch.empty(T, N, 512, device="cuda")
     gates = torch.empty(T, N, 2, 4, 256, device="cuda")
-    call("ocrs_gru_layer_fwd" + ("_persist" if backend == "persist" else ""), ptr(gi[0]), ptr(gi[1]), ptr(D["w_hh"]),
+    call("ocrs_gru_layer_fwd_persist", ptr(gi[0]), ptr(gi[1]), ptr(D["w_hh"]),
          ptr(D["w_hh_reverse"]), ptr(D["b_hh"]), ptr(D["b_hh_reverse"]), ptr(out), ptr(gates), T, N, st)
     assert rel_l2(out, ref) < 1e-5
     whhT = [D["w_hh" + s].t().contiguous() for s in ("", "_reverse")]
     dgi = [torch.empty(T * N, 768, device="cuda") for _ in range(2)]
     dgh = [torch.empty(T * N, 768, device="cuda") for _ in range(2)]
-    carry = torch.empty(2, N, 256, device="cuda")
     dd = dout.cuda()
-    if backend == "persist":
-        call("ocrs_gru_layer_bwd_persist", ptr(whhT[0]), ptr(whhT[1]), ptr(dd), ptr(out), ptr(gates), ptr(dgi[0]),
-             ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), T, N, st)
-    else:
-        call("ocrs_gru_layer_bwd", ptr(whhT[0]), ptr(whhT[1]), ptr(dd), ptr(out), ptr(gates), ptr(dgi[0]), ptr(dgi[1]),
-             ptr(dgh[0]), ptr(dgh[1]), ptr(carry), T, N, st)
+    call("ocrs_gru_layer_bwd_persist", ptr(whhT[0]), ptr(whhT[1]), ptr(dd), ptr(out), ptr(gates), ptr(dgi[0]),
+         ptr(dgi[1]), ptr(dgh[0]), ptr(dgh[1]), T, N, st)
     for d, s in enumerate(("", "_reverse")):
         assert rel_l2(dgi[d].sum(0), P64["b_ih" + s].grad) < 1e-4
         assert rel_l2(dgh[d].sum(0), P64["b_hh" + s].grad) < 1e-4
