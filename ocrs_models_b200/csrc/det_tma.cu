@@ -97,11 +97,25 @@ __device__ __forceinline__ bool tile_masks(int x0, int y0, int H, int W, int lan
   return border;
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): two independent multiply-adds per issue slot.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // One stage (FCH channels) of the forward block: depthwise 3x3 on the activated window, then the 1x1 contraction.
 template <bool XF, bool BORDER, int CO_T, int FCH>
 __device__ __forceinline__ void fwd_chunk(const float* st, const float* sdw, const float* spw, const float* sxf, int Cin,
                                           int c0, const bool (&rowok)[PPT + 2], const bool (&colok)[3],
-                                          float (&acc)[PPT][CO_T], float* dwo, size_t plane, int W, unsigned okmask) {
+                                          u64 (&acc)[PPT][CO_T / 2], float* dwo, size_t plane, int W, unsigned okmask) {
 #pragma unroll
   for (int c = 0; c < FCH; ++c) {
     float v[PPT + 2][3];
@@ -126,16 +140,19 @@ __device__ __forceinline__ void fwd_chunk(const float* st, const float* sdw, con
       for (int i = 0; i < PPT; ++i)
         if (okmask & (1u << i)) dwo[(size_t)ci * plane + (size_t)i * W] = d[i];
     }
+    // 1x1 contraction on packed FFMA2: (acc[o], acc[o+1]) += (d, d) * (w[o], w[o+1]) - half the issue slots of 64 FFMA
+    u64 dd[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) dd[i] = pack2(d[i], d[i]);
     const float4* w4 = reinterpret_cast<const float4*>(spw + ci * CO_T);
 #pragma unroll
     for (int o4 = 0; o4 < CO_T / 4; ++o4) {
       const float4 wv = w4[o4];
+      const u64 w01 = pack2(wv.x, wv.y), w23 = pack2(wv.z, wv.w);
 #pragma unroll
       for (int i = 0; i < PPT; ++i) {
-        acc[i][o4 * 4 + 0] = fmaf(d[i], wv.x, acc[i][o4 * 4 + 0]);
-        acc[i][o4 * 4 + 1] = fmaf(d[i], wv.y, acc[i][o4 * 4 + 1]);
-        acc[i][o4 * 4 + 2] = fmaf(d[i], wv.z, acc[i][o4 * 4 + 2]);
-        acc[i][o4 * 4 + 3] = fmaf(d[i], wv.w, acc[i][o4 * 4 + 3]);
+        acc[i][o4 * 2 + 0] = fma2(dd[i], w01, acc[i][o4 * 2 + 0]);
+        acc[i][o4 * 2 + 1] = fma2(dd[i], w23, acc[i][o4 * 2 + 1]);
       }
     }
   }
@@ -201,7 +218,7 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
   if (tid == 0)
     for (int j = 0; j < NSTAGE && j < total; ++j) issue(j);
 
-  float acc[PPT][CO_T];
+  u64 acc2[PPT][CO_T / 2];
   float stat = 0.f;  // lane l accumulates column l of (sum[0..CO_T), sumsq[0..CO_T)) over all tiles of this CTA
   bool rowok[PPT + 2], colok[3];
   bool border = false;
@@ -216,7 +233,7 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
 #pragma unroll
       for (int i = 0; i < PPT; ++i)
 #pragma unroll
-        for (int o = 0; o < CO_T; ++o) acc[i][o] = 0.f;
+        for (int o = 0; o < CO_T / 2; ++o) acc2[i][o] = 0ull;
       border = tile_masks(x0, y0, a.H, a.W, lane, warp, rowok, colok);
       if (a.dwo != nullptr && cot == 0) {
         const int gx = x0 + lane, gy0 = y0 + PPT * warp;
@@ -230,15 +247,20 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
     tma::mbar_wait(tma::smem_u32(&bars[s]), (j / NSTAGE) & 1);
     const float* st = stages + s * STAGE_FLOATS + (PPT * warp) * BW + lane + 3;
     const int c0 = ch * FCH;  // Cin is 1 (FCH = 1) or a multiple of FCH (checked on the host)
-    if (!has_xf) fwd_chunk<false, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc, dwo_t, plane, a.W, okmask);
-    else if (border) fwd_chunk<true, true, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc, dwo_t, plane, a.W, okmask);
-    else fwd_chunk<true, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc, dwo_t, plane, a.W, okmask);
+    if (!has_xf) fwd_chunk<false, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc2, dwo_t, plane, a.W, okmask);
+    else if (border) fwd_chunk<true, true, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc2, dwo_t, plane, a.W, okmask);
+    else fwd_chunk<true, false, CO_T, FCH>(st, sdw, spw, sxf, Cin, c0, rowok, colok, acc2, dwo_t, plane, a.W, okmask);
     __syncthreads();  // every thread is done with stage s
     if (tid == 0 && j + NSTAGE < total) issue(j + NSTAGE);
     if (++ch == nchunks) {
       ch = 0;
       ++k;
       const int gx = x0 + lane, gy0 = y0 + PPT * warp;
+      float acc[PPT][CO_T];
+#pragma unroll
+      for (int i = 0; i < PPT; ++i)
+#pragma unroll
+        for (int o = 0; o < CO_T / 2; ++o) unpack2(acc2[i][o], acc[i][2 * o], acc[i][2 * o + 1]);
       float sv[2 * CO_T];
       float* yp = a.y + (size_t)n * a.y_ss + ((size_t)co0 * a.H + gy0) * a.W + gx;  // Cout % CO_T == 0 (host check)
       const size_t HW = (size_t)a.H * a.W;
