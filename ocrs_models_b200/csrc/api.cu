@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "tma_util.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <string>
@@ -73,7 +74,11 @@ int ocrs_get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const unsig
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, d, st, b, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   // haloed boxes start 16 bytes before a 128-byte line and are 160 bytes wide: promoting every row to whole
+                   // 128-byte lines would fetch 256-384 bytes for 160 (measured: DRAM reads 2x the algorithmic bytes)
+                   // (no measurable effect on the kernels' time either way: they are bound by instruction issue)
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OCRS_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u", (int)r, rank,
                  dims[0], dims[1], box[0], box[1]);
   if (g_maps.size() > 4096) g_maps.clear();  // bound the cache if a caller never reuses addresses

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tma_util.cuh"
 #include <math.h>
+#include <type_traits>
 
 namespace {
 
@@ -57,12 +58,11 @@ struct TileWalk {  // spatial tiles (n, ty, tx) assigned round-robin to the CTAs
   int tiles_x, tiles_y, sp_total, sp0, sp_stride;
   __device__ __forceinline__ int count() const { return sp0 < sp_total ? (sp_total - sp0 + sp_stride - 1) / sp_stride : 0; }
   __device__ __forceinline__ void decode(int k, int& n, int& x0, int& y0) const {
-    const int sp = sp0 + k * sp_stride;
-    const int per = tiles_x * tiles_y;
-    n = sp / per;
-    const int r = sp - n * per;
-    y0 = (r / tiles_x) * TH;
-    x0 = (r % tiles_x) * TW;
+    const unsigned sp = (unsigned)(sp0 + k * sp_stride), per = (unsigned)(tiles_x * tiles_y);
+    const unsigned nn = sp / per, r = sp - nn * per, ry = r / (unsigned)tiles_x;  // unsigned: no sign fix-up code
+    n = (int)nn;
+    y0 = (int)ry * TH;
+    x0 = (int)(r - ry * (unsigned)tiles_x) * TW;
   }
 };
 
@@ -393,11 +393,18 @@ sep_dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_con
 #pragma unroll
     for (int q = 0; q < 9; ++q) dwacc[c][q] = 0.f;
   }
-  for (int j = 0; j < total; ++j) {
-    int n, x0, y0;
-    walk.decode(j, n, x0, y0);
+  // One tile. FULL: the tile and its halo lie inside the image (88 % of the tiles at 1024^2): no masks, no bounds checks.
+  auto tile_body = [&](auto full_tag, int j, int n, int x0, int y0) {
+    constexpr bool FULL = decltype(full_tag)::value;
     const int gx = x0 + lane, gy0 = y0 + PPT * warp;
-    const bool xok = gx < a.W;
+    const size_t plane = (size_t)a.H * a.W;
+    float* dx0 = a.dx + (size_t)n * a.dx_ss + ((size_t)c0 * a.H + gy0) * a.W + gx;
+    unsigned ok = (1u << PPT) - 1;  // which of this thread's PPT pixels are inside the image
+    if (!FULL) {
+      ok = 0;
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) ok |= (gx < a.W && gy0 + i < a.H) ? (1u << i) : 0u;
+    }
     // previous contents of dx (skip connections: two consumers accumulate): issue the loads before waiting
     float old[DCH][PPT];
 #pragma unroll
@@ -405,11 +412,10 @@ sep_dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_con
 #pragma unroll
       for (int i = 0; i < PPT; ++i) {
         old[c][i] = 0.f;
-        if (a.accumulate && xok && gy0 + i < a.H && c0 + c < a.C)
-          old[c][i] = a.dx[(size_t)n * a.dx_ss + ((size_t)(c0 + c) * a.H + gy0 + i) * a.W + gx];
+        if (a.accumulate && (FULL || ((ok >> i) & 1u)) && c0 + c < a.C) old[c][i] = dx0[c * plane + (size_t)i * a.W];
       }
     bool rowok[PPT + 2], colok[3];
-    const bool border = tile_masks(x0, y0, a.H, a.W, lane, warp, rowok, colok);
+    if (!FULL) tile_masks(x0, y0, a.H, a.W, lane, warp, rowok, colok);
     const int s = j % NSTAGE;
     tma::mbar_wait(tma::smem_u32(&bars[s]), (j / NSTAGE) & 1);
     const float* st = stages + s * STAGE_FLOATS + (PPT * warp) * BW + lane + 3;
@@ -418,9 +424,7 @@ sep_dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_con
       if (c0 + c >= a.C) continue;
       float gv[PPT + 2][3], xv[PPT + 2][3];
       load_window<false, false>(st + c * PLANE, 1.f, 0.f, 0.f, rowok, colok, gv);  // g is zero outside the image (TMA fill)
-      if (border) load_window<true, true>(st + XOFF + c * PLANE, sc[c], sh[c], lo[c], rowok, colok, xv);
-      else load_window<true, false>(st + XOFF + c * PLANE, sc[c], sh[c], lo[c], rowok, colok, xv);
-      float* dxp = a.dx + (size_t)n * a.dx_ss + ((size_t)(c0 + c) * a.H + gy0) * a.W + gx;
+      load_window<true, !FULL>(st + XOFF + c * PLANE, sc[c], sh[c], lo[c], rowok, colok, xv);
 #pragma unroll
       for (int i = 0; i < PPT; ++i) {
         // dx[p] = sum_k w[k] * g[p - (k - 1)]: window element (i + 2 - ky, 2 - kx)
@@ -429,14 +433,14 @@ sep_dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_con
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) t = fmaf(w[c][ky * 3 + kx], gv[i + 2 - ky][2 - kx], t);
-        if (xok && gy0 + i < a.H) {
+        if (FULL || ((ok >> i) & 1u)) {
           const float gc = gv[i + 1][1];
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) dwacc[c][ky * 3 + kx] = fmaf(gc, xv[i + ky][kx], dwacc[c][ky * 3 + kx]);
           const float o = t + old[c][i];
-          dxp[(size_t)i * a.W] = o;
+          dx0[c * plane + (size_t)i * a.W] = o;
           if (need_bn) {
             const float raw = st[XOFF + c * PLANE + (i + 1) * BW + 1];  // xv holds the activated value
             const float dz = (fmaf(raw, sc[c], sh[c]) > lo[c]) ? o : 0.f;
@@ -446,6 +450,13 @@ sep_dw_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_con
         }
       }
     }
+  };
+  for (int j = 0; j < total; ++j) {
+    int n, x0, y0;
+    walk.decode(j, n, x0, y0);
+    const bool full = x0 > 0 && y0 > 0 && x0 + TW + 1 <= a.W && y0 + TH + 1 <= a.H;  // uniform per CTA
+    if (full) tile_body(std::true_type{}, j, n, x0, y0);
+    else tile_body(std::false_type{}, j, n, x0, y0);
     __syncthreads();
     if (tid == 0 && j + NSTAGE < total) issue(j + NSTAGE);
   }
