@@ -730,10 +730,15 @@ struct PwWg2Args {
 // covers 512 contiguous bytes of ONE plane, where gathering straight in fragment layout touched 8 planes per
 // request and ran into the L1 tag rate) into a 4-stage ring of [48 planes][128 pixels] whose plane stride (132)
 // makes the fragment reads (8 planes x 4 pixels per warp request) bank-conflict free.
-constexpr int GPX = 128;           // pixels per stage
-constexpr int GPS = GPX + 4;       // plane stride in shared memory
 constexpr int GSTAGES = 4;
-constexpr int GPLANES = 48;        // d_a[16] | y[16] | dwo[16]
+// NPL = channel planes per operand group (d_a | y | dwo): 16, or 8 for the 8-channel blocks, which then take 256 pixels
+// per stage in the same shared memory (their stages were too short to hide the per-stage barrier latency).
+template <int NPL> struct GCfg {
+  static constexpr int GPX = NPL == 8 ? 256 : 128;   // pixels per stage
+  static constexpr int GPS = GPX + 4;                // plane stride in shared memory (= 4 mod 32)
+  static constexpr int GPLANES = 3 * NPL;
+  static constexpr int KSTEPS = GPX / 64;            // k-steps (8 pixels) per warp and stage
+};
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -742,11 +747,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int NPL>
 __global__ void __launch_bounds__(NTHREADS, 2)
 pw_wgrad_saved_kernel(PwWg2Args a) {
+  constexpr int GPX = GCfg<NPL>::GPX, GPS = GCfg<NPL>::GPS, GPLANES = GCfg<NPL>::GPLANES, KSTEPS = GCfg<NPL>::KSTEPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);  // [GSTAGES][GPLANES][GPS]; reused for the final reduction
-  float* gs = stages + GSTAGES * GPLANES * GPS;        // [16][GPS] staging of the fused data gradient
+  float* gs = stages + GSTAGES * GPLANES * GPS;        // [NPL][GPS] staging of the fused data gradient
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int cit = (a.Cin + 15) / 16;
   const int co0 = (blockIdx.y / cit) * 16, ci0 = (blockIdx.y % cit) * 16;
@@ -787,7 +794,7 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
   bool pok[GPLANES / 8];
 #pragma unroll
   for (int r = 0; r < GPLANES / 8; ++r) {
-    const int pl = warp + 8 * r, which = pl >> 4, ch = pl & 15;  // which: 0 = d_a, 1 = y, 2 = dwo
+    const int pl = warp + 8 * r, which = pl / NPL, ch = pl % NPL;  // which: 0 = d_a, 1 = y, 2 = dwo
     pok[r] = ch < (which == 2 ? nci : nco);
     pbase[r] = which == 0 ? a.d_a + (size_t)(co0 + ch) * a.HW : which == 1 ? a.y + (size_t)(co0 + ch) * a.HW
                                                                             : a.dwo + (size_t)(ci0 + ch) * a.HW;
@@ -797,19 +804,25 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
     const long long w = blockIdx.x + j * gridDim.x;
     const int n = (int)(w / chunks_per_n);
     const long long p0 = (w - (long long)n * chunks_per_n) * GPX + 4 * lane;
-    const long long rem = a.HW - p0;  // pixels left in the plane from this thread's column on
-    const int bytes = rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0);
-    const long long pc = rem > 0 ? p0 : 0;  // keep the (unread) source address inside the tensor
+    const long long pc = p0 < a.HW ? p0 : 0;  // keep the (unread) source address inside the tensor
     const long long off[3] = {(long long)n * a.da_ss + pc, (long long)n * a.y_ss + pc, (long long)n * dwo_ss + pc};
     const uint32_t dst = tma::smem_u32(stages + (j % GSTAGES) * (GPLANES * GPS) + 4 * lane + warp * GPS);
 #pragma unroll
     for (int r = 0; r < GPLANES / 8; ++r)
-      if (pok[r]) cp_async16(dst + r * 8 * GPS * 4, pbase[r] + off[r >> 1], bytes);  // bytes < 16 zero-fills a plane's tail
+      if (pok[r]) {
+        const int which = (warp + 8 * r) / NPL;
+#pragma unroll
+        for (int q = 0; q < GPX / 128; ++q) {  // 128 pixels = one 16-byte column per lane
+          const long long rem = a.HW - (p0 + 128 * q);
+          const int bytes = rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0);
+          cp_async16(dst + (r * 8 * GPS + 128 * q) * 4, pbase[r] + off[which] + (rem > 0 ? 128 * q : 0), bytes);  // bytes < 16 zero-fills
+        }
+      }
   };
   // planes of channels this CTA does not have (8-channel blocks, Cin = 1) are zeroed once and never requested
   for (int i = tid; i < GSTAGES * GPLANES * GPS; i += NTHREADS) {
-    const int pl = (i / GPS) % GPLANES, ch = pl & 15;
-    if (ch >= ((pl >> 4) == 2 ? nci : nco)) stages[i] = 0.f;
+    const int pl = (i / GPS) % GPLANES, ch = pl % NPL;
+    if (ch >= (pl / NPL == 2 ? nci : nco)) stages[i] = 0.f;
   }
   __syncthreads();
   for (int j = 0; j < GSTAGES - 1; ++j) {
@@ -823,15 +836,15 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
     cp_async_commit();
     float* st = stages + (j % GSTAGES) * (GPLANES * GPS);
 #pragma unroll
-    for (int u = 0; u < GPX / 64; ++u) {  // 16 k-steps per stage, 2 per warp: warp w owns pixels 16w .. 16w+15
-      const int px = (warp * (GPX / 64) + u) * 8 + t;
+    for (int u = 0; u < KSTEPS; ++u) {  // warp w owns pixels 8 KSTEPS w .. 8 KSTEPS (w + 1) - 1 of the stage
+      const int px = (warp * KSTEPS + u) * 8 + t;
       uint32_t ah[4], al[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // q: 0 = (g, t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
         const int h = q & 1, e = q >> 1;
-        if (8 * h >= nco) { ah[q] = 0u; al[q] = 0u; continue; }  // uniform: 8-channel blocks use half of the M tile
+        if (8 * h >= NPL || 8 * h >= nco) { ah[q] = 0u; al[q] = 0u; continue; }  // 8-channel blocks use half of the M tile
         const float da = st[(g + 8 * h) * GPS + px + 4 * e];
-        const float yv = st[(16 + g + 8 * h) * GPS + px + 4 * e];
+        const float yv = st[(NPL + g + 8 * h) * GPS + px + 4 * e];
         const float dz = (fmaf(yv, ksc[h], ksh[h]) > klo[h]) ? da : 0.f;
         // channels past nco have kk* = 0; pixels past HW give dy = k3 but meet a zero-filled dwo
         const float dy = fmaf(kk1[h], dz, fmaf(kk2[h], yv, kk3[h]));
@@ -840,10 +853,10 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
       }
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
-        if (8 * jj >= nci) continue;
+        if (8 * jj >= NPL || 8 * jj >= nci) continue;
         uint32_t bh0, bl0, bh1, bl1;
-        tf32_split2(st[(32 + 8 * jj + g) * GPS + px], bh0, bl0);      // (k = t,     n = ci 8jj + g)
-        tf32_split2(st[(32 + 8 * jj + g) * GPS + px + 4], bh1, bl1);  // (k = t + 4, n = ci 8jj + g)
+        tf32_split2(st[(2 * NPL + 8 * jj + g) * GPS + px], bh0, bl0);      // (k = t,     n = ci 8jj + g)
+        tf32_split2(st[(2 * NPL + 8 * jj + g) * GPS + px + 4], bh1, bl1);  // (k = t + 4, n = ci 8jj + g)
         mma_tf32_16n8k8(c[jj], al, bh0, bh1);
         mma_tf32_16n8k8(c[jj], ah, bl0, bl1);
         mma_tf32_16n8k8(c[jj], ah, bh0, bh1);
@@ -853,12 +866,12 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
       // g tile of this stage: warp w owns pixels 16w .. 16w+15 (two n-tiles of 8), all 16 input channels
       __syncwarp();
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int px = warp * 16 + nt * 8;
+      for (int nt = 0; nt < KSTEPS; ++nt) {
+        const int px = (warp * KSTEPS + nt) * 8;
         float cg[4] = {0.f, 0.f, 0.f, 0.f}, cx[4] = {0.f, 0.f, 0.f, 0.f};  // hi.hi and cross terms apart
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          if (8 * ks >= nco) continue;
+          if (8 * ks >= NPL || 8 * ks >= nco) continue;
           uint32_t bh[2], bl[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e)  // B: (k = t -> co 2t, k = t+4 -> co 2t+1; n = pixel g): dy written above
@@ -869,25 +882,25 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
         }
         // C fragment: c0 (ci g, px 2t), c1 (ci g, px 2t+1), c2 (ci g+8, px 2t), c3 (ci g+8, px 2t+1)
         *reinterpret_cast<float2*>(gs + g * GPS + px + 2 * t) = make_float2(cg[0] + cx[0], cg[1] + cx[1]);
-        *reinterpret_cast<float2*>(gs + (g + 8) * GPS + px + 2 * t) = make_float2(cg[2] + cx[2], cg[3] + cx[3]);
+        if (NPL > 8) *reinterpret_cast<float2*>(gs + (g + 8) * GPS + px + 2 * t) = make_float2(cg[2] + cx[2], cg[3] + cx[3]);
       }
       __syncthreads();  // gs complete (the loop-top barrier of the next stage protects its reuse)
       {
         const long long w = blockIdx.x + j * gridDim.x;
         const int n = (int)(w / chunks_per_n);
         const long long p0 = (w - (long long)n * chunks_per_n) * GPX + 4 * lane;
-        if (p0 < a.HW) {  // HW % 4 == 0: the four pixels are in or out together
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int ci = warp + 8 * r;
-            if (ci < nci)
-              *reinterpret_cast<float4*>(a.g + (size_t)n * a.g_ss + (size_t)(ci0 + ci) * a.HW + p0) =
-                  *reinterpret_cast<const float4*>(gs + ci * GPS + 4 * lane);
-          }
+        for (int r = 0; r < NPL / 8; ++r) {
+          const int ci = warp + 8 * r;
+#pragma unroll
+          for (int q = 0; q < GPX / 128; ++q)
+            if (ci < nci && p0 + 128 * q < a.HW)  // HW % 4 == 0: the four pixels are in or out together
+              *reinterpret_cast<float4*>(a.g + (size_t)n * a.g_ss + (size_t)(ci0 + ci) * a.HW + p0 + 128 * q) =
+                  *reinterpret_cast<const float4*>(gs + ci * GPS + 4 * lane + 128 * q);
         }
       }
     }
-    if ((j & 3) == 3) {  // keep the tensor core's truncating accumulation chains short (8 k-steps)
+    if ((j & (NPL == 8 ? 1 : 3)) == (NPL == 8 ? 1 : 3)) {  // keep the tensor core's truncating accumulation chains short (8 k-steps)
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
@@ -1193,7 +1206,8 @@ int ocrs_det_sep_pw_wgrad(const float* d_a, long long da_ss, const float* y, lon
 // Rows of the [workers][Cout][Cin] partials of ocrs_det_pw_wgrad_saved.
 int ocrs_det_pw_wgrad_saved_workers(int N, long long HW, int Cout, int Cin) {
   const int pairs = ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16);
-  const long long items = (long long)N * ((HW + GPX - 1) / GPX);
+  const int gpx = (Cout <= 8 && Cin <= 8) ? GCfg<8>::GPX : GCfg<16>::GPX;
+  const long long items = (long long)N * ((HW + gpx - 1) / gpx);
   long long per = (2 * OCRS_NUM_SMS + pairs - 1) / pairs;
   if (per > items) per = items;
   return (int)(per < 1 ? 1 : per);
@@ -1217,10 +1231,16 @@ int ocrs_det_pw_wgrad_saved(const float* d_a, long long da_ss, const float* y, l
   a.sc = sc; a.sh = sh; a.lo = lo; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.partials = partials;
   a.Cout = Cout; a.Cin = Cin; a.N = N; a.HW = HW;
   a.wpw = wpw; a.g = g; a.g_ss = g_ss;
-  const size_t smem = (size_t)GSTAGES * GPLANES * GPS * 4 + 16 * GPS * 4;
-  OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ocrs_det_pw_wgrad_saved_workers(N, HW, Cout, Cin), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
-  pw_wgrad_saved_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  if (Cout <= 8 && Cin <= 8) {
+    const size_t smem = (size_t)(GSTAGES * GCfg<8>::GPLANES + 8) * GCfg<8>::GPS * 4;
+    OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pw_wgrad_saved_kernel<8><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    const size_t smem = (size_t)(GSTAGES * GCfg<16>::GPLANES + 16) * GCfg<16>::GPS * 4;
+    OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pw_wgrad_saved_kernel<16><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  }
   OCRS_CHECK_LAUNCH("pw_wgrad_saved_kernel");
   return 0;
 }
