@@ -117,6 +117,24 @@ class Workload:
         self.dev = {k: v.to(device) for k, v in self.host.items()}
         self.units = self.host["image"].shape[0]
         self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in self.host.items() if k in ("image", "mask", "targets"))
+        self.graphed = None  # GraphedTrainStep once enable_graph() succeeded
+
+    def enable_graph(self):
+        """Capture the whole step into a CUDA graph (ocrs_models_b200.optim.GraphedTrainStep) and replay it from then
+        on: the eager step is bound by the host issuing ~280 launches, not by the kernels. Falls back to eager."""
+        from ocrs_models_b200.optim import GraphedTrainStep
+
+        def loss_from_batch(model, b):
+            if self.kind == "rec":
+                return self.loss_fn(model(b["image"]), b["targets"], b["input_lengths"], b["target_lengths"])
+            return self.loss_fn(model(b["image"]), b["mask"])
+
+        try:
+            self.graphed = GraphedTrainStep(self.model, self.opt, loss_from_batch, self.dev)
+        except Exception as e:  # noqa: BLE001 - any capture problem: keep measuring the eager step and say so
+            self.graphed = None
+            self.graph_error = f"{type(e).__name__}: {e}"[:300]
+        return self.graphed is not None
 
     def step(self, batch):
         self.opt.zero_grad()
@@ -129,11 +147,18 @@ class Workload:
         self.opt.step()
         return loss
 
+    def step_eager(self):
+        return self.step(self.dev)
+
     def step_resident(self):
+        if self.graphed is not None:
+            return self.graphed()
         return self.step(self.dev)
 
     def step_e2e(self):
         """Public-API step from HOST buffers: H2D of the inputs, the step, D2H of the loss."""
+        if self.graphed is not None:
+            return float(self.graphed({k: self.host[k] for k in ("image", "mask", "targets") if k in self.host}).item())
         b = dict(self.host)
         for k in ("image", "mask", "targets"):
             if k in b:
@@ -170,7 +195,7 @@ def kernel_profile(wl: Workload, steps=2):
 
     _lib.PROFILE = {}
     for _ in range(steps):
-        wl.step_resident()
+        wl.step_eager()
     torch.cuda.synchronize(wl.device)
     prof, _lib.PROFILE = _lib.PROFILE, None
     out = {}
@@ -404,6 +429,8 @@ def strong_scaling(args, device, rank, world, dist_on, global_batch=512):
     the weak-scaling headline (64 lines per GPU). Same step, device-timed, max over ranks."""
     per = global_batch // world
     wl = Workload("rec", device, rank, world, n=per)
+    if not args.no_graph:
+        wl.enable_graph()
     steps = max(3, min(args.steps, 10))
     ms, _ = timed(wl.step_resident, steps, 3, device, dist_on)
     del wl
@@ -411,6 +438,28 @@ def strong_scaling(args, device, rank, world, dist_on, global_batch=512):
     return {"metric": "train lines/sec rec@64x800, global batch 512 (strong scaling)", "global_batch": per * world,
             "per_gpu_batch": per, "value": per * world * steps / (ms * 1e-3), "unit": "lines/s", "ms_per_step": ms / steps,
             "steps": steps, "scaling": "strong"}
+
+
+def fast_mode(args, device, rank, world, dist_on):
+    """The labelled TF32 fast mode of the recognition path (rec_engine.set_precision("tf32")): same workload, ONE plain TF32
+    tensor-core product per k-step instead of 3xTF32. Not parity numerics (error measured by tests/test_fast_mode_gpu.py,
+    quoted in DESIGN.md); reported beside the headline, never as the headline."""
+    from ocrs_models_b200 import rec_engine
+
+    prev = rec_engine.set_precision("tf32")
+    try:
+        wl = Workload("rec", device, rank, world)
+        if not args.no_graph:
+            wl.enable_graph()
+        steps = max(3, min(args.steps, 10))
+        ms, _ = timed(wl.step_resident, steps, 3, device, dist_on)
+        units = wl.units * world
+        del wl
+        torch.cuda.empty_cache()
+    finally:
+        rec_engine.set_precision(prev)
+    return {"metric": "train lines/sec rec@64x800 (fast mode: plain TF32 GEMMs, NOT parity numerics)", "precision_mode": "tf32",
+            "value": units * steps / (ms * 1e-3), "unit": "lines/s", "ms_per_step": ms / steps, "steps": steps}
 
 
 def metric_name(kind):
@@ -430,7 +479,7 @@ def measure(kind, args, device, rank, world, dist_on, pk):
     lib = _lib.lib()
     # The very first step (initial weights, rank-0 batch) is checked against the loss the UNMODIFIED reference computes
     # for the same seeds in fp64 (tests/golden/bench_first_step.json, written by oracle/bench_constants.py).
-    first_loss = float(wl.step_resident().item())
+    first_loss = float(wl.step_eager().item())
     check = None
     if rank == 0:
         cpath = os.path.join(ROOT, "tests", "golden", "bench_first_step.json")
@@ -439,13 +488,15 @@ def measure(kind, args, device, rank, world, dist_on, pk):
         check = {"ours": first_loss, "reference_fp64": ref, "rel_err": rel, "tolerance": 1e-3}
         if not rel < 1e-3:
             raise SystemExit(f"bench.py: first-step {kind} loss {first_loss} differs from the reference's {ref} (rel {rel:.2e})")
+    graph_on = (not args.no_graph) and wl.enable_graph()
     for _ in range(max(args.warmup - 1, 0)):
         wl.step_resident()
     torch.cuda.synchronize(device)
     l0 = lib.ocrs_launch_count()
     with ClockSampler(device.index or 0, enabled=not args.no_clocks) as cs:
         ms, _ = timed(wl.step_resident, args.steps, 0, device, dist_on)
-    launches = lib.ocrs_launch_count() - l0
+    # replayed graph launches are not seen by the library's host-side counter: one replay = launches_per_step kernels
+    launches = wl.graphed.launches_per_step * args.steps if graph_on else lib.ocrs_launch_count() - l0
     _, wall = timed(wl.step_e2e, args.steps, 1, device, dist_on)
     units = wl.units * world
     unit = "lines/s" if kind == "rec" else "images/s"
@@ -454,6 +505,7 @@ def measure(kind, args, device, rank, world, dist_on, pk):
         "e2e": {"value": units * args.steps / (wall * 1e-3), "unit": unit, "h2d_bytes_per_step": wl.h2d_bytes,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": cs.summary(), "first_step_loss": check,
+        "cuda_graph": bool(graph_on) if graph_on else {"enabled": False, "why": getattr(wl, "graph_error", "--no-graph")},
     }
     prof = kernel_profile(wl)  # every rank: the step contains the gradient all-reduce
     if rank == 0:
@@ -487,6 +539,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the other workload's sub-object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cap", type=float, default=150.0, help="time cap in seconds of the --impl reference run")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-clocks", action="store_true",
                     help="do not start the nvidia-smi clock sampler (for runs under ncu, which follows child processes)")
     args = ap.parse_args()
@@ -510,6 +563,7 @@ def main():
     other_res = None if args.no_secondary else measure(other, args, device, rank, world, dist_on, pk)
 
     strong = None if (args.no_secondary or args.workload != "rec") else strong_scaling(args, device, rank, world, dist_on)
+    fast = None if (args.no_secondary or args.workload != "rec") else fast_mode(args, device, rank, world, dist_on)
     if rank == 0:
         line = {
             "metric": metric_name(args.workload),
@@ -519,13 +573,15 @@ def main():
             "config": {"workload": workload_name(args.workload), "parallelism": f"dp{world}", "l2": "inputs+activations > L2 (126 MB)",
                        "precision_mode": "parity: fp32 storage; 3xTF32 tcgen05 GEMMs (4 TMEM accumulators) + fp32 FMA elsewhere"},
             "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
-            "first_step_loss": main_res["first_step_loss"],
+            "first_step_loss": main_res["first_step_loss"], "cuda_graph": main_res["cuda_graph"],
             "roofline": main_res.get("roofline"), "step_roofline": main_res.get("step_roofline"),
             "ctc_roofline": main_res.get("ctc_roofline"),
             "kernel_ms_per_step": main_res.get("kernel_ms_per_step"),
         }
         if strong is not None:
             line["strong_scaling"] = strong
+        if fast is not None:
+            line["fast_mode_tf32"] = fast
         if other_res is not None:
             line[other] = {"metric": metric_name(other),
                            "workload": workload_name(other), **other_res}

@@ -71,6 +71,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_gemm_splits": [I, I],
     # tcgen05 GEMM (csrc/gemm_tc.cu)
+    "ocrs_gemm_tc_set_fast": [I],
     "ocrs_gemm_tc_supported": [P, L, P, L],
     "ocrs_gemm_tc": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_gemm_tc_splits": [I, I],
@@ -105,6 +106,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_optim_blocks": [],
     "ocrs_grad_norm": [P, L, F, P, P, P],
     "ocrs_adam_step": [P, P, P, P, L, F, F, F, F, I, F, F, P, P],
+    "ocrs_adam_step_dev": [P, P, P, P, L, F, F, F, F, P, F, F, P, P],
     # balanced BCE (csrc/det_loss.cu)
     "ocrs_bce_state_words": [],
     "ocrs_bce_blocks": [],

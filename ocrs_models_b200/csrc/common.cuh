@@ -41,6 +41,21 @@ void ocrs_count_launches(int n);
 
 static inline int ocrs_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device/context: do it once per (kernel, device), not once
+// per process (wrong with several GPUs in one process) and not on every call (microseconds of host time per launch
+// add up: the recognition step has ~280 launches). `flags` is a per-call-site array of 64 relaxed atomics.
+#define OCRS_SET_SMEM_ONCE(kernel, bytes)                                                                \
+  do {                                                                                                   \
+    static unsigned char flags__[64] = {0};                                                              \
+    int dev__ = 0;                                                                                       \
+    cudaGetDevice(&dev__);                                                                               \
+    dev__ &= 63;                                                                                         \
+    if (!__atomic_load_n(&flags__[dev__], __ATOMIC_ACQUIRE)) {                                           \
+      OCRS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      __atomic_store_n(&flags__[dev__], (unsigned char)1, __ATOMIC_RELEASE);                             \
+    }                                                                                                    \
+  } while (0)
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

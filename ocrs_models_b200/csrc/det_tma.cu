@@ -310,6 +310,7 @@ sep_fwd_tma_kernel(const __grid_constant__ CUtensorMap xmap, FwdArgs a) {
   }
 }
 
+constexpr int FWD_MAX_CIN = 256;  // the attribute is set once per device for the largest block of the network
 template <int CO_T, int FCH>
 size_t fwd_smem(int Cin) {
   return (size_t)NSTAGE * box_floats(FCH) * 4 + 64 + (size_t)Cin * (12 + CO_T + 3) * 4 + 8 * 2 * CO_T * 4 + 128;
@@ -1086,7 +1087,7 @@ int ocrs_det_tma_supported(const float* x, long long x_ss, const float* y, long 
 // 1 when ocrs_det_sep_fwd handles these channel counts (Cout a multiple of its 8/16-channel tile, Cin < 4 or a multiple of 4).
 int ocrs_det_sep_channels_ok(int Cin, int Cout) {
   const int cot = Cout <= 8 ? 8 : 16;
-  return Cout % cot == 0 && (Cin < 4 || Cin % 4 == 0);
+  return Cout % cot == 0 && (Cin < 4 || Cin % 4 == 0) && Cin <= FWD_MAX_CIN;
 }
 
 // Rows of the [rows][2][Cout] statistics partials ocrs_det_sep_fwd writes.
@@ -1103,7 +1104,8 @@ int ocrs_det_sep_fwd(const float* x, long long x_ss, int N, int Cin, int H, int 
   OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "sep_fwd: bad dims");
   OCRS_CHECK_ARG(ocrs_det_tma_supported(x, x_ss, y, y_ss, H, W), "sep_fwd: views are not TMA-addressable");
   const int cot = Cout <= 8 ? 8 : 16;
-  OCRS_CHECK_ARG(Cout % cot == 0 && (Cin < 4 || Cin % 4 == 0), "sep_fwd: channel counts %d -> %d unsupported (ocrs_det_sep_channels_ok)", Cin, Cout);
+  OCRS_CHECK_ARG(Cout % cot == 0 && (Cin < 4 || Cin % 4 == 0) && Cin <= FWD_MAX_CIN,
+                 "sep_fwd: channel counts %d -> %d unsupported (ocrs_det_sep_channels_ok)", Cin, Cout);
   FwdArgs a;
   a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.N = N; a.n_cot = ocrs_cdiv(Cout, cot);
   a.in_scale = in_scale; a.in_shift = in_shift; a.in_lo = in_lo; a.wdw = wdw; a.wpw = wpw;
@@ -1117,22 +1119,22 @@ int ocrs_det_sep_fwd(const float* x, long long x_ss, int N, int Cin, int H, int 
     if (ocrs_plane_map(&xmap, x, x_ss, N, Cin, H, W, BW, BH, 1)) return -1;
     const size_t smem = fwd_smem<8, 1>(Cin);
     if (cot == 8) {
-      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      OCRS_SET_SMEM_ONCE((sep_fwd_tma_kernel<8, 1>), (fwd_smem<8, 1>(FWD_MAX_CIN)));
       sep_fwd_tma_kernel<8, 1><<<ctas, NTHREADS, smem, st>>>(xmap, a);
     } else {
       const size_t smem16 = fwd_smem<16, 1>(Cin);
-      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      OCRS_SET_SMEM_ONCE((sep_fwd_tma_kernel<16, 1>), (fwd_smem<16, 1>(FWD_MAX_CIN)));
       sep_fwd_tma_kernel<16, 1><<<ctas, NTHREADS, smem16, st>>>(xmap, a);
     }
   } else {
     if (ocrs_plane_map(&xmap, x, x_ss, N, Cin, H, W, BW, BH, 4)) return -1;
     if (cot == 8) {
       const size_t smem = fwd_smem<8, 4>(Cin);
-      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      OCRS_SET_SMEM_ONCE((sep_fwd_tma_kernel<8, 4>), (fwd_smem<8, 4>(FWD_MAX_CIN)));
       sep_fwd_tma_kernel<8, 4><<<ctas, NTHREADS, smem, st>>>(xmap, a);
     } else {
       const size_t smem = fwd_smem<16, 4>(Cin);
-      OCRS_CUDA(cudaFuncSetAttribute(sep_fwd_tma_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      OCRS_SET_SMEM_ONCE((sep_fwd_tma_kernel<16, 4>), (fwd_smem<16, 4>(FWD_MAX_CIN)));
       sep_fwd_tma_kernel<16, 4><<<ctas, NTHREADS, smem, st>>>(xmap, a);
     }
   }
@@ -1166,7 +1168,7 @@ int ocrs_det_sep_dw_bwd(const float* g, long long g_ss, const float* x, long lon
   if (ocrs_plane_map(&gmap, g, g_ss, N, C, H, W, BW, BH, DCH)) return -1;
   if (ocrs_plane_map(&xmap, x, x_ss, N, C, H, W, BW, BH, DCH)) return -1;
   const size_t smem = (size_t)NSTAGE * 2 * box_floats(DCH) * 4 + 64 + 8 * DCH * 11 * 4 + 128;
-  OCRS_CUDA(cudaFuncSetAttribute(sep_dw_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OCRS_SET_SMEM_ONCE(sep_dw_bwd_tma_kernel, smem);
   const int ctas = a.ctas_per_chunk * ocrs_cdiv(C, DCH);
   sep_dw_bwd_tma_kernel<<<ctas, NTHREADS, smem, (cudaStream_t)stream>>>(gmap, xmap, a);
   OCRS_CHECK_LAUNCH("sep_dw_bwd_tma_kernel");
@@ -1196,7 +1198,7 @@ int ocrs_det_sep_pw_wgrad(const float* d_a, long long da_ss, const float* y, lon
   if (ocrs_plane_map(&xmap, x, x_ss, N, Cin, H, W, BW, WBH, WCH)) return -1;
   const int pairs = ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16);
   const size_t smem = (size_t)2 * box_floats2(WCH * WPLANE) * 4 + 64 + (size_t)WCH * XS_PLANE * 4 + 8 * 256 * 4 + 48 * 4 + 128;
-  OCRS_CUDA(cudaFuncSetAttribute(sep_pw_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OCRS_SET_SMEM_ONCE(sep_pw_wgrad_tma_kernel, smem);
   dim3 grid(pw_wgrad_workers(N, H, W, pairs), pairs);
   sep_pw_wgrad_tma_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(xmap, a);
   OCRS_CHECK_LAUNCH("sep_pw_wgrad_tma_kernel");
@@ -1234,11 +1236,11 @@ int ocrs_det_pw_wgrad_saved(const float* d_a, long long da_ss, const float* y, l
   dim3 grid(ocrs_det_pw_wgrad_saved_workers(N, HW, Cout, Cin), ocrs_cdiv(Cout, 16) * ocrs_cdiv(Cin, 16));
   if (Cout <= 8 && Cin <= 8) {
     const size_t smem = (size_t)(GSTAGES * GCfg<8>::GPLANES + 8) * GCfg<8>::GPS * 4;
-    OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCRS_SET_SMEM_ONCE(pw_wgrad_saved_kernel<8>, smem);
     pw_wgrad_saved_kernel<8><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   } else {
     const size_t smem = (size_t)(GSTAGES * GCfg<16>::GPLANES + 16) * GCfg<16>::GPS * 4;
-    OCRS_CUDA(cudaFuncSetAttribute(pw_wgrad_saved_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCRS_SET_SMEM_ONCE(pw_wgrad_saved_kernel<16>, smem);
     pw_wgrad_saved_kernel<16><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   }
   OCRS_CHECK_LAUNCH("pw_wgrad_saved_kernel");
@@ -1272,7 +1274,7 @@ int ocrs_det_convt_wgrad_staged(const float* x, long long x_ss, int N, int Cin, 
   a.Cin = Cin; a.Cout = Cout; a.Hin = Hin; a.Win = Win; a.Hs = Hs; a.Ws = Ws; a.N = N;
   size_t smem = (size_t)2 * CT_STAGE * 4;
   if (smem < 8 * 1152 * 4) smem = 8 * 1152 * 4;
-  OCRS_CUDA(cudaFuncSetAttribute(convt_wgrad_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OCRS_SET_SMEM_ONCE(convt_wgrad_staged_kernel, smem);
   dim3 grid(ocrs_det_convt_wgrad_staged_workers(N, Hin, Win, Cin, Cout), ocrs_cdiv(Cin, 16) * ocrs_cdiv(Cout, 8));
   convt_wgrad_staged_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   OCRS_CHECK_LAUNCH("convt_wgrad_staged_kernel");

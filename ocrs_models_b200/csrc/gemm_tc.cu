@@ -56,6 +56,8 @@ struct TcArgs {
   int tiles_m, tiles_n, zs;  // tile grid walked by the persistent CTAs
   int nbuf;                  // TMEM accumulator sets (2 when 4*bn <= 256 columns)
   int b_split;               // B arrives pre-split (map_b = TF32-exact hi, map_b2 = lo): weights, split once per step
+  int fast;                  // labelled throughput mode: ONE plain TF32 product per k-step (the tensor core truncates the
+                             // fp32 operands to 10 mantissa bits), no hi/lo split, 1/3 of the MMAs; NOT parity numerics
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -266,8 +268,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t bl = make_desc(sb + A_TILE_BYTES + ks * b_step, b_lbo, b_sbo, b_lt);
             // accumulator columns: [0,bn) [bn,2bn) [2bn,3bn) = hi.hi round-robin, [3bn,4bn) = cross terms
             umma_tf32(tb + (uint32_t)((i % 3) * g.bn), ah, bh, g.idesc, (i >= 3 || ks > 0) ? 1u : 0u);
-            umma_tf32(tb + (uint32_t)(3 * g.bn), ah, bl, g.idesc, (i > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32(tb + (uint32_t)(3 * g.bn), al, bh, g.idesc, 1u);
+            if (!g.fast) {
+              umma_tf32(tb + (uint32_t)(3 * g.bn), ah, bl, g.idesc, (i > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32(tb + (uint32_t)(3 * g.bn), al, bh, g.idesc, 1u);
+            }
           }
           umma_commit(empty_bar(s));
         }
@@ -343,9 +347,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int iy = woy + wdy[q], ix = wox + wdx[q];
             kb_[q] = kb_[q] && wchunk[q] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW;
           }
+          if (g.fast) continue;
           va[q] = ah[j];
           vb[q] = (j < b_vec) ? bh[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (g.fast) {
+          // fast mode: the operands stay as they landed; only out-of-image rows of the implicit convolutions are zeroed
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = ct + 256 * q;
+            if (!ka[q]) ah[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (CONV == 2 && j < b_vec && !kb_[q]) bh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = ct + 256 * q;
@@ -391,11 +405,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c0 = 0; c0 < g.bn; c0 += 32) {
         uint32_t r0[32], r1[32];
         float v[32];
-        tmem_ld32(lane_addr + (uint32_t)(3 * g.bn + c0), r0);  // cross terms (smallest magnitude first)
+        if (!g.fast) tmem_ld32(lane_addr + (uint32_t)(3 * g.bn + c0), r0);  // cross terms (smallest magnitude first)
         tmem_ld32(lane_addr + (uint32_t)c0, r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        for (int j = 0; j < 32; ++j) v[j] = (g.fast ? 0.f : __uint_as_float(r0[j])) + __uint_as_float(r1[j]);
         if (n_main > 1) {
           tmem_ld32(lane_addr + (uint32_t)(g.bn + c0), r0);
           if (n_main > 2) tmem_ld32(lane_addr + (uint32_t)(2 * g.bn + c0), r1);
@@ -532,11 +546,12 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restri
   lo[i] = v - h;
 }
 
+int g_fast_mode = 0;  // process-wide numerics mode of the tensor-core GEMMs (ocrs_gemm_tc_set_fast)
+
 template <int CONV>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mb2, TcArgs g, int tiles_n, int tiles_m, int zs,
               cudaStream_t st, const char* what) {
-  // per device/context attribute, set on every call (cheap, thread-safe, correct with several GPUs per process)
-  OCRS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OCRS_SET_SMEM_ONCE(gemm_tc_kernel<CONV>, SMEM_BYTES);
   g.tiles_m = tiles_m;
   g.tiles_n = tiles_n;
   g.zs = zs;
@@ -544,6 +559,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* m
   const long long total = (long long)tiles_m * tiles_n * zs;
   const int ctas = (int)(total < OCRS_NUM_SMS ? total : OCRS_NUM_SMS);
   g.b_split = mb2 != nullptr;
+  g.fast = g_fast_mode;
   gemm_tc_kernel<CONV><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
   OCRS_CHECK_LAUNCH(what);
   return 0;
@@ -552,6 +568,16 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* m
 }  // namespace
 
 extern "C" {
+
+// Numerics mode of every tensor-core GEMM / implicit convolution launched afterwards by this process:
+// 0 (default) = parity mode, 3xTF32 with four TMEM accumulators (fp32-class accuracy, what every parity test runs);
+// 1 = labelled fast mode, one plain TF32 product (operands truncated to 10 mantissa bits by the tensor core, relative
+// error ~1e-3 per product). Pre-split weight operands must not be used in fast mode. Returns the previous mode.
+int ocrs_gemm_tc_set_fast(int fast) {
+  const int prev = g_fast_mode;
+  g_fast_mode = fast ? 1 : 0;
+  return prev;
+}
 
 // 1 when (lda, ldb, pointers) satisfy the TMA constraints of ocrs_gemm_tc.
 int ocrs_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb) {

@@ -453,9 +453,8 @@ int ocrs_gru_layer_fwd_persist(const float* gi_f, const float* gi_r, const float
                                const float* bhh_f, const float* bhh_r, float* out, float* gates, int T, int N,
                                void* stream) {
   OCRS_CHECK_ARG(T > 0 && N > 0, "gru_layer_fwd_persist: bad dims");
-  // per device/context attribute, set on every call (cheap, thread-safe, correct with several GPUs per process)
-  OCRS_CUDA(cudaFuncSetAttribute(gru_fwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-  OCRS_CUDA(cudaFuncSetAttribute(gru_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  OCRS_SET_SMEM_ONCE(gru_fwd_persist_kernel<true>, FWD_SMEM);
+  OCRS_SET_SMEM_ONCE(gru_fwd_persist_kernel<false>, FWD_SMEM);
   const int groups = ocrs_cdiv(N, RB);
   FwdArgs a{{gi_f, gi_r}, {whh_f, whh_r}, {bhh_f, bhh_r}, out, gates, T, N, groups};
   int rc = launch_cluster(use_async() ? gru_fwd_persist_kernel<true> : gru_fwd_persist_kernel<false>, a, 2 * groups,
@@ -470,9 +469,8 @@ int ocrs_gru_layer_bwd_persist(const float* whhT_f, const float* whhT_r, const f
                                const float* gates, float* dgi_f, float* dgi_r, float* dgh_f, float* dgh_r, int T,
                                int N, void* stream) {
   OCRS_CHECK_ARG(T > 0 && N > 0, "gru_layer_bwd_persist: bad dims");
-  // per device/context attribute, set on every call (cheap, thread-safe, correct with several GPUs per process)
-  OCRS_CUDA(cudaFuncSetAttribute(gru_bwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-  OCRS_CUDA(cudaFuncSetAttribute(gru_bwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+  OCRS_SET_SMEM_ONCE(gru_bwd_persist_kernel<true>, BWD_SMEM);
+  OCRS_SET_SMEM_ONCE(gru_bwd_persist_kernel<false>, BWD_SMEM);
   const int groups = ocrs_cdiv(N, RB);
   BwdArgs a{{whhT_f, whhT_r}, dout, out, gates, {dgi_f, dgi_r}, {dgh_f, dgh_r}, T, N, groups};
   int rc = launch_cluster(use_async() ? gru_bwd_persist_kernel<true> : gru_bwd_persist_kernel<false>, a, 2 * groups,

@@ -55,6 +55,28 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// Same update with the step count read from device memory (CUDA-graph friendly: the bias corrections change every
+// replay without re-recording the launch). step_dev holds the number of steps already taken.
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                long long n, float lr, float b1, float b2, float eps, const int* __restrict__ step_dev,
+                float grad_scale, float max_norm, const float* __restrict__ norm) {
+  const float t = (float)(step_dev[0] + 1);
+  const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  float coef = grad_scale;
+  if (max_norm > 0.f) coef *= fminf(max_norm / (norm[0] + 1e-6f), 1.f);
+  const float step = lr / bc1;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[i] * coef;
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+__global__ void step_inc_kernel(int* step_dev) { step_dev[0] += 1; }
+
 }  // namespace
 
 extern "C" {
@@ -83,6 +105,19 @@ int ocrs_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
   adam_kernel<<<ocrs_optim_blocks(), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, bc1,
                                                                     bc2_sqrt, grad_scale, max_norm, norm);
   OCRS_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+
+// ocrs_adam_step with the step counter in device memory: uses step_dev[0] + 1 as the step and increments it afterwards
+// (so a captured CUDA graph of the training step stays valid across replays).
+int ocrs_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                       int* step_dev, float grad_scale, float max_norm, const float* norm, void* stream) {
+  OCRS_CHECK_ARG(step_dev != nullptr, "adam_step_dev: needs the device step counter");
+  OCRS_CHECK_ARG(max_norm <= 0.f || norm != nullptr, "adam_step_dev: clipping needs the gradient norm");
+  adam_dev_kernel<<<ocrs_optim_blocks(), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, step_dev,
+                                                                        grad_scale, max_norm, norm);
+  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  OCRS_CHECK_LAUNCH_N("adam_dev_kernel", 2);
   return 0;
 }
 

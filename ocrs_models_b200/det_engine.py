@@ -414,6 +414,8 @@ def detection_forward(model, x: torch.Tensor) -> torch.Tensor:
     if plan is None:
         plan = _Plan(model)
         model.__dict__["_plan"] = plan
-    _lib.check_module_tensors(model, x.device, "DetectionModel")
+    if model.__dict__.get("_ocrs_checked") != x.device:
+        _lib.check_module_tensors(model, x.device, "DetectionModel")
+        model.__dict__["_ocrs_checked"] = x.device
     x = x.float().contiguous()
     return _DetFunction.apply(plan, x, *plan.all_params())

@@ -38,7 +38,16 @@ def _double(cin: int, cout: int) -> nn.Module:
     return _holder(seq=nn.Sequential(_separable(cin, cout), _separable(cout, cout)))
 
 
-class DetectionModel(nn.Module):
+class _Validated(nn.Module):
+    """Parameters/buffers are checked (device, dtype, contiguity) on the first forward after any `_apply`
+    (.to / .cuda / .half / memory_format changes all go through it), not on every call."""
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_ocrs_checked", None)
+        return super()._apply(fn, *args, **kwargs)
+
+
+class DetectionModel(_Validated):
     """Text-detection U-Net (depthwise-separable), greyscale NCHW in, text probability out."""
 
     def __init__(self):
@@ -59,7 +68,7 @@ class DetectionModel(nn.Module):
         return detection_forward(self, x)
 
 
-class RecognitionModel(nn.Module):
+class RecognitionModel(_Validated):
     """CRNN: conv backbone -> 2-layer BiGRU -> linear -> log-softmax; (W//4+1, N, classes) out."""
 
     def __init__(self, alphabet: str):

@@ -57,6 +57,7 @@ class FusedAdam:
         self.max_grad_norm = max_grad_norm
         self.group, self.world = process_group, world_size
         self.t = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)  # steps taken, for the CUDA-graph path
         lib = _lib.lib()
         self.partials = torch.empty(lib.ocrs_optim_blocks(), dtype=torch.float32, device=dev)
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -90,6 +91,61 @@ class FusedAdam:
         with torch.cuda.device(self.dev):
             if clip > 0:
                 call("ocrs_grad_norm", ptr(self.flat_g), self.n, scale, ptr(self.partials), ptr(self.norm), st)
-            call("ocrs_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n, self.lr,
-                 self.betas[0], self.betas[1], self.eps, self.t, scale, clip, ptr(self.norm), st)
+            # the step count lives on the device (bias corrections are computed in the kernel), so the same recorded
+            # launch is valid for every replay of a captured step; self.t mirrors it on the host for eager use
+            call("ocrs_adam_step_dev", ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), self.n, self.lr,
+                 self.betas[0], self.betas[1], self.eps, ptr(self.step_dev), scale, clip, ptr(self.norm), st)
         return self.norm if clip > 0 else None
+
+
+class GraphedTrainStep:
+    """One whole training step (zero_grad -> forward -> loss -> backward -> [all-reduce] -> clip + Adam) captured ONCE into
+    a CUDA graph and replayed: the recognition step is ~280 kernel launches of ~30 us each, and the Python / ctypes /
+    autograd work that issues them costs about as much host time as the GPU needs to run them, so eager execution is
+    launch-bound as soon as the kernels get faster. Replay costs one cudaGraphLaunch.
+
+    Requirements (checked or documented): fixed batch shapes; the batch lives in the static device buffers this object
+    owns (`load(batch)` copies into them, host tensors should be pinned); lengths of the CTC loss are passed as DEVICE
+    tensors (a pageable host->device copy cannot be recorded). BatchNorm running statistics, `num_batches_tracked`,
+    the Adam moments and the device step counter advance on every replay exactly as in eager mode.
+    """
+
+    def __init__(self, model: torch.nn.Module, opt: FusedAdam, loss_from_batch, example_batch: dict, warmup: int = 3):
+        """loss_from_batch(model, batch_dict_of_static_device_tensors) -> scalar loss tensor."""
+        self.model, self.opt, self.loss_fn = model, opt, loss_from_batch
+        dev = opt.dev
+        self.static = {k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in example_batch.items()}
+        lib = _lib.lib()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture: lazy initialisation, allocator pools, TMA descriptors
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = lib.ocrs_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+        self.launches_per_step = int(lib.ocrs_launch_count() - l0)  # kernels of this library inside one replay
+
+    def _eager(self):
+        self.opt.zero_grad()
+        loss = self.loss_fn(self.model, self.static)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def load(self, batch: dict):
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                self.static[k].copy_(v, non_blocking=True)
+
+    def __call__(self, batch: dict | None = None) -> torch.Tensor:
+        """Replay the step (after copying `batch` into the static buffers when given). Returns the device loss tensor of
+        this step (overwritten by the next replay)."""
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        self.opt.t += 1
+        return self.loss

@@ -32,6 +32,25 @@ IMPLICIT = os.environ.get("OCRS_IMPLICIT", "1") == "1"
 PRESPLIT = os.environ.get("OCRS_PRESPLIT", "1") == "1"
 
 
+def set_precision(mode: str) -> str:
+    """Numerics mode of the recognition path's tensor-core GEMMs: "parity" (default: 3xTF32 + four TMEM accumulators,
+    fp32-class accuracy, what the 1e-3 parity claim and every headline number refer to) or "tf32" (labelled fast
+    mode: one plain TF32 product per k-step - the numerics class of what reference train_rec.py:118 runs on a GPU under
+    autocast, NOT parity numerics; GRU recurrence, BatchNorm statistics, CTC and the optimiser stay fp32).
+    Returns the previous mode. Also selectable with OCRS_PRECISION=tf32."""
+    global PRESPLIT, _PRECISION
+    if mode not in ("parity", "tf32"):
+        raise ValueError("precision mode must be 'parity' or 'tf32'")
+    prev = _PRECISION
+    _lib.lib().ocrs_gemm_tc_set_fast(int(mode == "tf32"))
+    PRESPLIT = mode == "parity" and os.environ.get("OCRS_PRESPLIT", "1") == "1"
+    _PRECISION = mode
+    return prev
+
+
+_PRECISION = "parity"
+
+
 class Split:
     """A weight matrix split for the 3xTF32 GEMM: `hi` (TF32-exact) and `lo` (remainder), same layout."""
 
@@ -425,7 +444,15 @@ class _RecFunction(torch.autograd.Function):
         return (None, None) + tuple(grads.get(id(p)) for p in model.parameters())
 
 
+_env_mode_applied = False
+
+
 def recognition_forward(model, x: torch.Tensor) -> torch.Tensor:
+    global _env_mode_applied
+    if not _env_mode_applied:
+        _env_mode_applied = True
+        if os.environ.get("OCRS_PRECISION", "parity") == "tf32":
+            set_precision("tf32")
     if not x.is_cuda:
         raise RuntimeError("ocrs_models_b200.RecognitionModel has no CPU path: input must be a CUDA tensor")
     if x.dim() != 4 or x.shape[1] != 1:
@@ -436,6 +463,8 @@ def recognition_forward(model, x: torch.Tensor) -> torch.Tensor:
         # conv.0's backward kernel produces weight/bias gradients only; refuse rather than return a silent zero
         raise RuntimeError("ocrs_models_b200.RecognitionModel does not compute the gradient w.r.t. the input image "
                            "(x.requires_grad must be False)")
-    _lib.check_module_tensors(model, x.device, "RecognitionModel")
+    if model.__dict__.get("_ocrs_checked") != x.device:
+        _lib.check_module_tensors(model, x.device, "RecognitionModel")
+        model.__dict__["_ocrs_checked"] = x.device
     x = x.float().contiguous()
     return _RecFunction.apply(model, x, *model.parameters())
