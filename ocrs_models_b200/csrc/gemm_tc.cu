@@ -140,7 +140,7 @@ constexpr int EPI_THREAD0 = 320;
 // The stage ring and its mbarrier phases run continuously across tiles, so the TMA producer and the
 // converter warps prefetch the next tile while the epilogue warps drain the finished accumulators; with
 // 4*bn <= 256 TMEM columns the accumulators are double-buffered and the drain is hidden completely.
-template <int CONV>
+template <int CONV, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b2, TcArgs g) {
@@ -268,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t bl = make_desc(sb + A_TILE_BYTES + ks * b_step, b_lbo, b_sbo, b_lt);
             // accumulator columns: [0,bn) [bn,2bn) [2bn,3bn) = hi.hi round-robin, [3bn,4bn) = cross terms
             umma_tf32(tb + (uint32_t)((i % 3) * g.bn), ah, bh, g.idesc, (i >= 3 || ks > 0) ? 1u : 0u);
-            if (!g.fast) {
+            if (!FAST) {
               umma_tf32(tb + (uint32_t)(3 * g.bn), ah, bl, g.idesc, (i > 0 || ks > 0) ? 1u : 0u);
               umma_tf32(tb + (uint32_t)(3 * g.bn), al, bh, g.idesc, 1u);
             }
@@ -347,11 +347,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int iy = woy + wdy[q], ix = wox + wdx[q];
             kb_[q] = kb_[q] && wchunk[q] && iy >= 0 && iy < g.cH && ix >= 0 && ix < g.cW;
           }
-          if (g.fast) continue;
+          if (FAST) continue;
           va[q] = ah[j];
           vb[q] = (j < b_vec) ? bh[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (g.fast) {
+        if (FAST) {
           // fast mode: the operands stay as they landed; only out-of-image rows of the implicit convolutions are zeroed
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -405,11 +405,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c0 = 0; c0 < g.bn; c0 += 32) {
         uint32_t r0[32], r1[32];
         float v[32];
-        if (!g.fast) tmem_ld32(lane_addr + (uint32_t)(3 * g.bn + c0), r0);  // cross terms (smallest magnitude first)
+        if (!FAST) tmem_ld32(lane_addr + (uint32_t)(3 * g.bn + c0), r0);  // cross terms (smallest magnitude first)
         tmem_ld32(lane_addr + (uint32_t)c0, r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (g.fast ? 0.f : __uint_as_float(r0[j])) + __uint_as_float(r1[j]);
+        for (int j = 0; j < 32; ++j) v[j] = (FAST ? 0.f : __uint_as_float(r0[j])) + __uint_as_float(r1[j]);
         if (n_main > 1) {
           tmem_ld32(lane_addr + (uint32_t)(g.bn + c0), r0);
           if (n_main > 2) tmem_ld32(lane_addr + (uint32_t)(2 * g.bn + c0), r1);
@@ -551,7 +551,8 @@ int g_fast_mode = 0;  // process-wide numerics mode of the tensor-core GEMMs (oc
 template <int CONV>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* mb2, TcArgs g, int tiles_n, int tiles_m, int zs,
               cudaStream_t st, const char* what) {
-  OCRS_SET_SMEM_ONCE(gemm_tc_kernel<CONV>, SMEM_BYTES);
+  OCRS_SET_SMEM_ONCE((gemm_tc_kernel<CONV, false>), SMEM_BYTES);
+  OCRS_SET_SMEM_ONCE((gemm_tc_kernel<CONV, true>), SMEM_BYTES);
   g.tiles_m = tiles_m;
   g.tiles_n = tiles_n;
   g.zs = zs;
@@ -560,7 +561,8 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* m
   const int ctas = (int)(total < OCRS_NUM_SMS ? total : OCRS_NUM_SMS);
   g.b_split = mb2 != nullptr;
   g.fast = g_fast_mode;
-  gemm_tc_kernel<CONV><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
+  if (g.fast) gemm_tc_kernel<CONV, true><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
+  else gemm_tc_kernel<CONV, false><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
   OCRS_CHECK_LAUNCH(what);
   return 0;
 }
