@@ -83,8 +83,12 @@ class FusedAdam:
 
     def step(self):
         """Returns the (device) gradient-norm tensor when clipping is on, else None."""
-        st = _lib.stream_ptr(self.dev)
         self.sync_gradients()
+        return self.apply_update()
+
+    def apply_update(self):
+        """Norm + clip + Adam on the (already reduced) flat gradient bucket: the part of `step()` after the collective."""
+        st = _lib.stream_ptr(self.dev)
         scale = 1.0 / self.world
         self.t += 1
         clip = self.max_grad_norm if self.max_grad_norm is not None else -1.0
@@ -123,18 +127,34 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # Multi-GPU: the NCCL all-reduce stays OUTSIDE the graphs (graph 1 = zero_grad + forward + loss + backward, eager
+        # all-reduce of the flat bucket, graph 2 = norm + clip + Adam): three host calls per step instead of ~300, and no
+        # collective is ever recorded (capturing NCCL inside the step graph hung the 2-GPU bench).
+        self.split = opt.world > 1
         self.graph = torch.cuda.CUDAGraph()
         l0 = lib.ocrs_launch_count()
         with torch.cuda.graph(self.graph):
-            self.loss = self._eager()
+            self.loss = self._fwd_bwd()
+            if not self.split:
+                self.opt.step()
+        self.graph2 = None
+        if self.split:
+            self.opt.sync_gradients()
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2):
+                self.opt.apply_update()
         self.launches_per_step = int(lib.ocrs_launch_count() - l0)  # kernels of this library inside one replay
 
-    def _eager(self):
+    def _fwd_bwd(self):
         self.opt.zero_grad()
         loss = self.loss_fn(self.model, self.static)
         loss.backward()
-        self.opt.step()
         return loss.detach()
+
+    def _eager(self):
+        loss = self._fwd_bwd()
+        self.opt.step()
+        return loss
 
     def load(self, batch: dict):
         for k, v in batch.items():
@@ -147,5 +167,9 @@ class GraphedTrainStep:
         if batch is not None:
             self.load(batch)
         self.graph.replay()
+        if self.split:
+            self.opt._synced = False
+            self.opt.sync_gradients()
+            self.graph2.replay()
         self.opt.t += 1
         return self.loss
