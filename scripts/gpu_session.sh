@@ -30,6 +30,6 @@ full)
   timeout -s KILL 120 $NCU --set full --import-source on -k regex:'gemm_tc' -c 6 -o $O/rec_gemm_full -f python scripts/one_step.py rec > /dev/null 2>&1
   timeout -s KILL 120 $NCU --set full --import-source on -k regex:'gru_' -c 4 -o $O/rec_gru_full -f python scripts/one_step.py rec > /dev/null 2>&1
   timeout -s KILL 90 $NCU --set full --import-source on -k regex:'ctc_alpha|ctc_beta' -o $O/ctc_full -f python scripts/one_step.py ctc 8192 > /dev/null 2>&1
-  timeout -s KILL 150 $NCU --set full --import-source on -k regex:'pw_wgrad|dwpw_fwd|dw_bwd|pwT_bwd|bnrelu_bwd' -c 8 -o $O/det_full -f python scripts/one_step.py det 8 > /dev/null 2>&1 ;;
+  timeout -s KILL 150 $NCU --set full --import-source on -k regex:'sep_fwd|pw_wgrad_saved|sep_dw_bwd|convt_wgrad_staged' -s 6 -c 8 -o $O/det_full -f python scripts/one_step.py det 8 > /dev/null 2>&1 ;;
 esac; done
 du -sh $O; ls -la $O
