@@ -90,15 +90,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Wait for the st.async payload of the peers. The data arrives through the async proxy and is made visible by the
+// mbarrier's transaction completion itself, so the default CTA-scope acquire is enough; `.acquire.cluster` made the
+// compiler emit CCTL.IVALL (an L1 invalidate, 10 % of the backward kernel's stall samples) on every step and threw
+// away the L1 lines the prefetches below bring in.
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -331,6 +336,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) gru_bwd_persist_kernel(BwdArgs
       const float* gs = p.gates + (((size_t)t * N + n) * 2 + d) * 4 * H;
       r = gs[u]; z = gs[H + u]; nn = gs[2 * H + u]; ghn = gs[3 * H + u];
       if (tprev >= 0 && tprev < T) hp = p.out[((size_t)tprev * N + n) * 512 + d * H + u];
+      // next step's operands: the register file is full (the loads above get sunk below the product), so bring the
+      // lines into L1 now and let the loads of the next step hit
+      const int t2 = d == 0 ? t - 1 : t + 1;
+      if (t2 >= 0 && t2 < T) {
+        prefetch_l1(p.dout + ((size_t)t2 * N + n) * 512 + d * H + u);
+        const float* gs2 = p.gates + (((size_t)t2 * N + n) * 2 + d) * 4 * H;
+        prefetch_l1(gs2 + u); prefetch_l1(gs2 + H + u); prefetch_l1(gs2 + 2 * H + u); prefetch_l1(gs2 + 3 * H + u);
+        const int t3 = d == 0 ? t2 - 1 : t2 + 1;
+        if (t3 >= 0 && t3 < T) prefetch_l1(p.out + ((size_t)t3 * N + n) * 512 + d * H + u);
+      }
     }
     if (ASYNC && s > 0) {
       mbar_wait_cluster(mbar + 8 * buf, (uint32_t)((s - 1) >> 1) & 1u);
