@@ -102,6 +102,9 @@ SIGNATURES: dict[str, list] = {
     "ocrs_ctc_greedy_cer": [P, I, I, I, P, P, L, I, I, P, P, P, P, P],
     # input pipeline (csrc/data.cu)
     "ocrs_collate_lines": [P, I, P, P, I, I, I, P, P],
+    # eval-path post-processing (csrc/postprocess.cu)
+    "ocrs_cc_label": [P, F, I, I, I, P, P, P, P],
+    "ocrs_cc_boundary": [P, I, I, I, P, I, P, P],
     # optimiser glue (csrc/optim.cu)
     "ocrs_optim_blocks": [],
     "ocrs_grad_norm": [P, L, F, P, P, P],
