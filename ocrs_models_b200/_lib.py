@@ -27,6 +27,7 @@ SIGNATURES: dict[str, list] = {
     # detection forward (csrc/det_fwd.cu)
     "ocrs_det_dwpw_partial_rows": [I, I, I],
     "ocrs_det_dwpw_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, P, P],
+    "ocrs_det_dw3x3_fwd": [P, L, I, I, I, I, P, P, P, P, P, P],
     "ocrs_bn_finalize": [P, I, I, D, P, P, P, P, F, F, I, I, P, P, P, P, P, P],
     "ocrs_det_pool2_fwd": [P, L, I, I, I, I, P, P, P, P, L, P],
     "ocrs_det_convt_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, I, I, P],
@@ -38,6 +39,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_reduce_rows": [I, L],
     "ocrs_bnrelu_bwd_reduce": [P, L, P, L, I, I, L, P, P, P, P, P, P, P],
     "ocrs_bn_bwd_finalize": [P, I, I, D, P, P, P, P, P, P, P, P, I, P],
+    "ocrs_det_dy": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, P],
     "ocrs_det_pwT_bwd": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, I, P, L, P],
     "ocrs_det_pw_wgrad_workers": [I, I, I],
     "ocrs_det_pw_wgrad": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, L, I, P, P, P, P, P, P],
@@ -75,6 +77,8 @@ SIGNATURES: dict[str, list] = {
     "ocrs_gemm_tc_supported": [P, L, P, L],
     "ocrs_gemm_tc": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_gemm_tc_splits": [I, I],
+    "ocrs_gemm_tc_batched": [P, L, I, I, I, P, L, I, I, I, P, L, L, I, I, I, I, P, P],
+    "ocrs_gemm_tc_batched_stat_rows": [I, I],
     "ocrs_gemm_tc_presplit": [P, L, I, P, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_conv3x3_tc_presplit": [P, I, I, I, I, P, P, I, P, L, P, I, P, P],
     "ocrs_split_tf32": [P, P, P, L, P],

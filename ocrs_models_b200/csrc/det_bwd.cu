@@ -173,6 +173,18 @@ __device__ __forceinline__ float dy_of(float da, float yv, float s, float t, flo
   return fmaf(a1, dz, fmaf(a2, yv, a3));
 }
 
+// dy materialised (levels with >= 64 channels: operand of the batched tcgen05 GEMMs): dy[n][co][p], contiguous.
+__global__ void __launch_bounds__(256)
+dy_kernel(const float* __restrict__ d_a, long long da_ss, const float* __restrict__ y, long long y_ss, int C,
+          long long HW, DyCoef k, float* __restrict__ dy) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.y, n = blockIdx.z;
+  if (i >= HW) return;
+  const size_t off = (size_t)c * HW + i;
+  dy[((size_t)n * C + c) * HW + i] = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], k.sc[c], k.sh[c],
+                                           k.lo[c], k.k1[c], k.k2[c], k.k3[c]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // g[ci] = sum_co Wpw[co][ci] * dy[co]. Thread = VEC consecutive pixels, CI_T input channels.
 constexpr int PWT_CO_CHUNK = 16;
@@ -902,6 +914,18 @@ int ocrs_bn_bwd_finalize(const float* partials, int nblk, int C, double count, c
   bn_bwd_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(partials, nblk, C, count, gamma, mean,
                                                               invstd, dgamma, dbeta, k1, k2, k3, training);
   OCRS_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return 0;
+}
+
+// dy = k1 * dz + k2 * y + k3 (BatchNorm + ReLU backward of d_a) written contiguously as [N][Cout][HW]: the operand
+// of the batched tcgen05 GEMMs for the 1x1 data and weight gradients of the levels with >= 64 channels.
+int ocrs_det_dy(const float* d_a, long long da_ss, const float* y, long long y_ss, int N, int Cout, long long HW,
+                const float* sc, const float* sh, const float* lo, const float* k1, const float* k2, const float* k3,
+                float* dy, void* stream) {
+  DyCoef k{sc, sh, lo, k1, k2, k3};
+  dim3 grid(ocrs_cdiv(HW, 256), Cout, N);
+  dy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, HW, k, dy);
+  OCRS_CHECK_LAUNCH("dy_kernel");
   return 0;
 }
 

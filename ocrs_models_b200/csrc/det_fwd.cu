@@ -318,9 +318,45 @@ __global__ void outconv_fwd_kernel(const float* __restrict__ x, long long x_ss, 
   prob[(size_t)n * HW + i] = 1.f / (1.f + expf(-z));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Depthwise 3x3 alone (levels with >= 64 channels, where the 1x1 contraction runs as a batched tcgen05 GEMM):
+// out[n][c][p] = dw3x3(xform(x))[n][c][p], contiguous [N][C][H][W].
+__global__ void __launch_bounds__(256)
+dw3x3_fwd_kernel(const float* __restrict__ x, long long x_ss, int C, int H, int W, const float* __restrict__ sc,
+                 const float* __restrict__ sh, const float* __restrict__ lo, const float* __restrict__ wdw,
+                 float* __restrict__ out) {
+  const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+  const int c = blockIdx.z % C, n = blockIdx.z / C;
+  if (px >= W || py >= H) return;
+  const float* xp = x + (size_t)n * x_ss + (size_t)c * H * W;
+  float s = 1.f, t = 0.f, l = -INFINITY;
+  if (sc) { s = sc[c]; t = sh[c]; l = lo[c]; }
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = py + ky - 1, xx = px + kx - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        acc = fmaf(xform_apply(xp[(size_t)yy * W + xx], s, t, l), wdw[(size_t)c * 9 + ky * 3 + kx], acc);
+    }
+  out[((size_t)n * C + c) * H * W + (size_t)py * W + px] = acc;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Depthwise 3x3 (pad 1, bias-free, reference models.py:12-17) of the activated input, written contiguously as
+// [N][C][H][W]: the B operand of ocrs_gemm_tc_batched for the 1x1 convolution of the levels with >= 64 channels.
+int ocrs_det_dw3x3_fwd(const float* x, long long x_ss, int N, int C, int H, int W, const float* sc, const float* sh,
+                       const float* lo, const float* wdw, float* out, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "dw3x3_fwd: bad dims");
+  dim3 block(32, 8), grid(ocrs_cdiv(W, 32), ocrs_cdiv(H, 8), N * C);
+  dw3x3_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, wdw, out);
+  OCRS_CHECK_LAUNCH("dw3x3_fwd_kernel");
+  return 0;
+}
 
 // Number of per-block statistic partial rows ocrs_det_dwpw_fwd writes ([rows][2][Cout] floats).
 int ocrs_det_dwpw_partial_rows(int N, int H, int W) {

@@ -56,6 +56,12 @@ struct TcArgs {
   int tiles_m, tiles_n, zs;  // tile grid walked by the persistent CTAs
   int nbuf;                  // TMEM accumulator sets (2 when 4*bn <= 256 columns)
   int b_split;               // B arrives pre-split (map_b = TF32-exact hi, map_b2 = lo): weights, split once per step
+  // Batched GEMM (detection deep levels): tile index z = batch item. Operands are 2-D matrices in which the items are
+  // stacked along the ROW axis of the tensor map (planar [N][C][HW] tensors: row = n*C + c), so an item is a row offset;
+  // every item runs the full K range; C advances by c_zstride elements per item.
+  int batched, a_brows, b_brows;
+  long long c_zstride;       // elements between consecutive z slices of C (split-K partials: M * ldc)
+  float* row_stats;          // [zs * tiles_n][2][M] per-row sum / sum of squares of the tile's columns (BatchNorm over N), or null
   int fast;                  // labelled throughput mode: ONE plain TF32 product per k-step (the tensor core truncates the
                              // fp32 operands to 10 mantissa bits), no hi/lo split, 1/3 of the MMAs; NOT parity numerics
 };
@@ -189,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tn_ = (tile_) % g.tiles_n, tr_ = (tile_) / g.tiles_n;  \
   const int tm_ = tr_ % g.tiles_m, tz_ = tr_ / g.tiles_m;          \
   const int m0 = tm_ * TBM, n0 = tn_ * g.bn;                       \
-  const int kb0 = tz_ * g.kb_per_split;                            \
+  const int kb0 = g.batched ? 0 : tz_ * g.kb_per_split;            \
   const int nkb = min(total_kb, kb0 + g.kb_per_split) - kb0;       \
   (void)m0; (void)n0; (void)kb0; (void)tz_; (void)tm_;
 
@@ -215,9 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int cpb = g.cC / TBK, kb = kb0 + i;
             const int tap = kb / cpb, c0 = (kb - tap * cpb) * TBK;
             tma_load_2d(sa, &map_a, c0, m0 + (tap / 3 - 1) * g.cW + (tap % 3 - 1), full_bar(s));
-          } else if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0, full_bar(s));
+          } else if (!g.a_mn) tma_load_2d(sa, &map_a, k0, m0 + tz_ * g.a_brows, full_bar(s));
           else
-            for (int c = 0; c < TBM / 32; ++c) tma_load_2d(sa + c * 4096, &map_a, m0 + 32 * c, k0, full_bar(s));
+            for (int c = 0; c < TBM / 32; ++c) tma_load_2d(sa + c * 4096, &map_a, m0 + 32 * c, k0 + tz_ * g.a_brows, full_bar(s));
           if (CONV == 2) {
             for (int c = 0; c < g.bn / 32; ++c) {
               const int col = n0 + 32 * c;
@@ -227,10 +233,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           } else if (!g.b_mn) {
-            tma_load_2d(sb, &map_b, k0, n0, full_bar(s));
+            tma_load_2d(sb, &map_b, k0, n0 + tz_ * g.b_brows, full_bar(s));
             if (g.b_split) tma_load_2d(sb + A_TILE_BYTES, &map_b2, k0, n0, full_bar(s));
           } else {
-            for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0, full_bar(s));
+            for (int c = 0; c < g.bn / 32; ++c) tma_load_2d(sb + c * 4096, &map_b, n0 + 32 * c, k0 + tz_ * g.b_brows, full_bar(s));
             if (g.b_split)
               for (int c = 0; c < g.bn / 32; ++c)
                 tma_load_2d(sb + A_TILE_BYTES + c * 4096, &map_b2, n0 + 32 * c, k0, full_bar(s));
@@ -399,7 +405,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = m0 + q * 32 + lane;   // output row held by this thread
       const bool row_ok = m < g.M;
-      float* crow = g.C + (size_t)tz_ * g.M * g.ldc + (size_t)(row_ok ? m : 0) * g.ldc;
+      float* crow = g.C + (size_t)tz_ * g.c_zstride + (size_t)(row_ok ? m : 0) * g.ldc;
+      float rs1 = 0.f, rs2 = 0.f;  // row statistics of this tile (g.row_stats)
       const int n_main = min(3, nkb);
       const uint32_t lane_addr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < g.bn; c0 += 32) {
@@ -435,6 +442,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (g.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (g.row_stats) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < g.N) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
         }
         if (row_ok) {
           if (vec_ok) {
@@ -479,6 +491,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           dst[lane] = s1;
           dst[32 + lane] = s2;
         }
+      }
+      if (g.row_stats && row_ok) {
+        const size_t blk = (size_t)tz_ * g.tiles_n + tn_;
+        g.row_stats[(blk * 2) * g.M + m] = rs1;
+        g.row_stats[(blk * 2 + 1) * g.M + m] = rs2;
       }
       if (g.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -561,6 +578,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* m
   const int ctas = (int)(total < OCRS_NUM_SMS ? total : OCRS_NUM_SMS);
   g.b_split = mb2 != nullptr;
   g.fast = g_fast_mode;
+  if (!g.batched) g.c_zstride = (long long)g.M * g.ldc;
   if (g.fast) gemm_tc_kernel<CONV, true><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
   else gemm_tc_kernel<CONV, false><<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2 ? *mb2 : mb, g);
   OCRS_CHECK_LAUNCH(what);
@@ -629,6 +647,40 @@ int ocrs_gemm_tc_presplit(const float* A, long long lda, int a_kmajor, const flo
   OCRS_CHECK_ARG(B_lo != nullptr, "gemm_tc_presplit: B_lo is null");
   return gemm_tc_impl(A, lda, a_kmajor, B_hi, B_lo, ldb, b_kmajor, C, ldc, M, N, K, bias, relu, accumulate, stats, splits, stream);
 }
+
+// Batched C[z] = op(A[z]) op(B[z]) on the same tcgen05 kernel, z < batch, for operands whose items are stacked along
+// the row axis of a 2-D matrix (planar NCHW activations: row = n*C + c, row pitch H*W). a_brows / b_brows = rows per
+// item (0: the operand is shared by all items, e.g. a weight matrix); a_rows / b_rows = total rows of the 2-D matrix.
+// a_kmajor: A rows are M (each row K long), else rows are K (each row M long); same for B with N. C[z] starts at
+// C + z * c_batch_stride, row pitch ldc. row_stats (optional): [batch * ceil(N / bn)][2][M] per-row sums and sums of
+// squares (BatchNorm statistics over N when the rows are channels). Used by the detection levels with >= 64 channels.
+int ocrs_gemm_tc_batched(const float* A, long long lda, int a_kmajor, int a_rows, int a_brows, const float* B,
+                         long long ldb, int b_kmajor, int b_rows, int b_brows, float* C, long long ldc,
+                         long long c_batch_stride, int M, int N, int K, int batch, float* row_stats, void* stream) {
+  OCRS_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tc_batched: bad dims");
+  OCRS_CHECK_ARG(ocrs_gemm_tc_supported(A, lda, B, ldb), "gemm_tc_batched: operands must be 16-byte aligned with ld %% 4 == 0");
+  OCRS_CHECK_ARG(K % TBK == 0 || (a_brows == 0 && b_brows == 0) || (a_kmajor && b_kmajor),
+                 "gemm_tc_batched: K must be a multiple of 32 when items are stacked along K rows");
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  CUtensorMap ma, mb;
+  if (a_kmajor) { if (make_map(&ma, A, K, a_rows, lda, TBK, TBM, false)) return -1; }
+  else          { if (make_map(&ma, A, M, a_rows, lda, 32, TBK, true)) return -1; }
+  if (b_kmajor) { if (make_map(&mb, B, K, b_rows, ldb, TBK, bn, false)) return -1; }
+  else          { if (make_map(&mb, B, N, b_rows, ldb, 32, TBK, true)) return -1; }
+  TcArgs g{C, ldc, M, N, K, nullptr, 0, 0, nullptr, 0, !a_kmajor, !b_kmajor, bn, 0, 0, 0, 0, 0};
+  g.kb_per_split = ocrs_cdiv(K, TBK);
+  g.batched = 1;
+  g.a_brows = a_brows;
+  g.b_brows = b_brows;
+  g.c_zstride = c_batch_stride;
+  g.row_stats = row_stats;
+  g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
+            ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  return launch_tc<0>(ma, mb, nullptr, g, ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), batch, (cudaStream_t)stream, "gemm_tc_kernel(batched)");
+}
+
+// Rows of the row_stats partials of ocrs_gemm_tc_batched.
+int ocrs_gemm_tc_batched_stat_rows(int N, int batch) { return batch * ocrs_cdiv(N, N <= 32 ? 32 : (N <= 64 ? 64 : 128)); }
 
 // hi[i] = src[i] rounded to TF32, lo[i] = src[i] - hi[i]: the operand split of the 3xTF32 GEMM, done once per
 // step for weight matrices.

@@ -26,6 +26,9 @@ USE_TMA = os.environ.get("OCRS_DET_TMA", "1") == "1"
 FUSE_BN_REDUCE = os.environ.get("OCRS_DET_FUSE_BN", "1") == "1"
 # 1x1 data gradient computed inside the weight-gradient kernel for blocks with <= 16 output channels (OCRS_DET_FUSE_PWT=0: separate pass).
 FUSE_PWT = os.environ.get("OCRS_DET_FUSE_PWT", "1") == "1"
+# Levels with >= 64 channels: depthwise 3x3 as its own kernel, the 1x1 convolution and both its gradients as batched
+# tcgen05 GEMMs (csrc/gemm_tc.cu). OCRS_DET_TC=0 keeps the CUDA-core kernels there too.
+USE_TC_DEEP = os.environ.get("OCRS_DET_TC", "1") == "1"
 # Keep each block's depthwise output from the forward pass for its 1x1 weight gradient (OCRS_DET_SAVE_DW=0: recompute it).
 SAVE_DW = os.environ.get("OCRS_DET_SAVE_DW", "1") == "1"
 BN_EPS = 1e-5
@@ -83,6 +86,8 @@ class _Sep:
             y = new_view(N, self.cout, H, W, dev)
         lib = _lib.lib()
         dwo = None
+        if self._tc_ok(inp, y, H, W):
+            return self._forward_tc(inp, y, N, H, W, training, st, xf_dst, save)
         tma = (USE_TMA and bool(lib.ocrs_det_tma_supported(inp.p, inp.ss, y.p, y.ss, H, W))
                and bool(lib.ocrs_det_sep_channels_ok(self.cin, self.cout)))
         meta = 4.0 * N * H * W * (self.cin + self.cout)
@@ -115,6 +120,55 @@ class _Sep:
             save[id(self)] = (inp, y, stats, bool(training), dwo)
         return y
 
+    # ---- levels with >= 64 channels: the 1x1 convolution and its two gradients are GEMMs (M = channels, N = pixels)
+    # on the tcgen05 kernel of the recognition path (csrc/gemm_tc.cu, batched over the samples of the planar layout) ----
+    def _tc_ok(self, inp: View, y: View, H, W):
+        HW = H * W
+        return (USE_TC_DEEP and self.cout >= 64 and self.cin >= 32 and self.cin % 32 == 0 and self.cout % 4 == 0
+                and HW % 4 == 0 and HW >= 64 and y.ss % 4 == 0 and y.p % 16 == 0)
+
+    def _forward_tc(self, inp: View, y: View, N, H, W, training, st, xf_dst, save):
+        dev = inp.t.device
+        lib = _lib.lib()
+        HW, ci, co = H * W, self.cin, self.cout
+        dwo = torch.empty((N, ci, H, W), dtype=torch.float32, device=dev)
+        call("ocrs_det_dw3x3_fwd", inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), ptr(dwo), st,
+             meta=8.0 * N * HW * ci)
+        rows = lib.ocrs_gemm_tc_batched_stat_rows(HW, N)
+        partials = torch.empty((rows, 2, co), dtype=torch.float32, device=dev) if training else None
+        call("ocrs_gemm_tc_batched", ptr(self.pw.weight), ci, 1, co, 0, ptr(dwo), HW, 0, N * ci, ci, y.p, HW, y.ss,
+             co, HW, ci, N, ptr(partials), st, meta=2.0 * N * HW * ci * co)
+        if xf_dst is None:
+            buf = torch.empty((3, co), dtype=torch.float32, device=dev)
+            xf_dst = (buf[0], buf[1], buf[2])
+        stats = torch.empty((2, co), dtype=torch.float32, device=dev)
+        bn = self.bn
+        call("ocrs_bn_finalize", ptr(partials), rows, co, float(N * HW), ptr(bn.weight), ptr(bn.bias),
+             ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, int(training), 1,
+             xf_dst[0].data_ptr(), xf_dst[1].data_ptr(), xf_dst[2].data_ptr(), ptr(stats[0]), ptr(stats[1]), st)
+        if training:
+            bn.num_batches_tracked.add_(1)
+        y.xf = xf_dst
+        if save is not None:
+            save[id(self)] = (inp, y, stats, bool(training), ("tc", dwo))
+        return y
+
+    def _pw_backward_tc(self, d_a: View, y: View, k, dwo, N, H, W, st):
+        """dy -> g = W^T dy and dW = sum_n dy x^T as batched tcgen05 GEMMs. Returns (g view, d_wpw)."""
+        dev = y.t.device
+        HW, ci, co = H * W, self.cin, self.cout
+        dy = torch.empty((N, co, HW), dtype=torch.float32, device=dev)
+        call("ocrs_det_dy", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(dy), st, meta=12.0 * N * HW * co)
+        g = new_view(N, ci, H, W, dev)
+        call("ocrs_gemm_tc_batched", ptr(self.pw.weight), ci, 0, co, 0, ptr(dy), HW, 0, N * co, co, g.p, HW, g.ss,
+             ci, HW, co, N, None, st, meta=2.0 * N * HW * ci * co)
+        wpart = torch.empty((N, co, ci), dtype=torch.float32, device=dev)
+        call("ocrs_gemm_tc_batched", ptr(dy), HW, 1, N * co, co, ptr(dwo), HW, 1, N * ci, ci, ptr(wpart), ci, co * ci,
+             co, ci, HW, N, None, st, meta=2.0 * N * HW * ci * co)
+        d_wpw = torch.empty_like(self.pw.weight)
+        _finalize(wpart, N, co * ci, d_wpw, st)
+        return g, d_wpw
+
     def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False, bn_pending=None):
         """d_a: gradient w.r.t. this block's activated output. Writes the gradient w.r.t. the
         block's (activated) input into `dx`; returns [d_wdw, d_wpw, d_gamma, d_beta].
@@ -139,30 +193,33 @@ class _Sep:
         call("ocrs_bn_bwd_finalize", ptr(part), rows, co, float(N * HW), ptr(self.bn.weight), ptr(stats[0]),
              ptr(stats[1]), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), int(training), st)
         k = (ysc, ysh, ylo, ptr(coef[2]), ptr(coef[3]), ptr(coef[4]))
-        g = new_view(N, ci, H, W, dev)
-        fuse_g = dwo is not None and co <= 16 and FUSE_PWT  # the weight-gradient kernel also emits g (csrc/det_tma.cu)
-        if not fuse_g:
-            call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
-                 meta=4.0 * N * HW * (2 * co + ci))
-        if dwo is not None:
-            workers = lib.ocrs_det_pw_wgrad_saved_workers(N, HW, co, ci)
-            wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
-            call("ocrs_det_pw_wgrad_saved", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(dwo), ci, ptr(wpart),
-                 ptr(self.pw.weight) if fuse_g else None, g.p if fuse_g else None, g.ss, st,
-                 meta=4.0 * N * HW * (2 * co + ci + (ci if fuse_g else 0)))
-            del dwo
-        elif USE_TMA and lib.ocrs_det_tma_supported(inp.p, inp.ss, inp.p, inp.ss, H, W):
-            workers = lib.ocrs_det_sep_pw_wgrad_workers(N, H, W, co, ci)
-            wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
-            call("ocrs_det_sep_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
-                 ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
+        if isinstance(dwo, tuple):  # levels with >= 64 channels: batched tcgen05 GEMMs
+            g, d_wpw = self._pw_backward_tc(d_a, y, k, dwo[1], N, H, W, st)
         else:
-            workers = lib.ocrs_det_pw_wgrad_workers(N, H, W)
-            wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
-            call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
-                 ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
-        d_wpw = torch.empty_like(self.pw.weight)
-        _finalize(wpart, workers, co * ci, d_wpw, st)
+            g = new_view(N, ci, H, W, dev)
+            fuse_g = dwo is not None and co <= 16 and FUSE_PWT  # the weight-gradient kernel also emits g (csrc/det_tma.cu)
+            if not fuse_g:
+                call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
+                     meta=4.0 * N * HW * (2 * co + ci))
+            if dwo is not None:
+                workers = lib.ocrs_det_pw_wgrad_saved_workers(N, HW, co, ci)
+                wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+                call("ocrs_det_pw_wgrad_saved", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(dwo), ci, ptr(wpart),
+                     ptr(self.pw.weight) if fuse_g else None, g.p if fuse_g else None, g.ss, st,
+                     meta=4.0 * N * HW * (2 * co + ci + (ci if fuse_g else 0)))
+            elif USE_TMA and lib.ocrs_det_tma_supported(inp.p, inp.ss, inp.p, inp.ss, H, W):
+                workers = lib.ocrs_det_sep_pw_wgrad_workers(N, H, W, co, ci)
+                wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+                call("ocrs_det_sep_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
+                     ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
+            else:
+                workers = lib.ocrs_det_pw_wgrad_workers(N, H, W)
+                wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+                call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
+                     ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
+            d_wpw = torch.empty_like(self.pw.weight)
+            _finalize(wpart, workers, co * ci, d_wpw, st)
+        dwo = None
         if dx is None:
             dx = new_view(N, ci, H, W, dev)
         d_wdw = torch.empty_like(self.dw.weight)

@@ -33,7 +33,9 @@ def _apply_xf(x, xf):
                                                          # TMA-addressable shapes (W % 4 == 0): csrc/det_tma.cu
                                                          (2, 1, 8, 40, 36, False), (1, 16, 16, 68, 100, True), (2, 32, 16, 96, 64, True),
                                                          (1, 64, 32, 32, 40, True), (1, 16, 32, 36, 44, True), (1, 256, 128, 8, 16, True),
-                                                         (3, 8, 8, 33, 132, True)])
+                                                         (3, 8, 8, 33, 132, True),
+                                                         # >= 64 channels: batched tcgen05 GEMMs (csrc/gemm_tc.cu)
+                                                         (2, 64, 64, 16, 16, True), (3, 32, 64, 24, 20, True), (2, 128, 256, 8, 8, True)])
 def test_separable_block_fwd_bwd(N, cin, cout, H, W, with_xf):
     from ocrs_models_b200.det_engine import View, _Sep, new_view
     from ocrs_models_b200.models import _separable

@@ -315,3 +315,42 @@ def test_runs_under_autocast_like_train_rec():
     assert lp.dtype == torch.float32 and torch.isfinite(loss)
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("case", ["fwd", "dgrad", "wgrad"])
+@pytest.mark.parametrize("N,cin,cout,HW", [(3, 64, 128, 1024), (2, 256, 256, 256), (4, 32, 64, 4096)])
+def test_batched_gemm_on_planar_activations(case, N, cin, cout, HW):
+    """ocrs_gemm_tc_batched: the three contractions of a 1x1 convolution on planar [N][C][HW] tensors (detection levels
+    with >= 64 channels): y = W x (+ per-channel row statistics), g = W^T dy, dW = sum_n dy x^T; vs fp64 einsum."""
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200._lib import call, ptr
+
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(N * cin + HW)
+    W = torch.randn(cout, cin, generator=g) * 0.1
+    x = torch.randn(N, cin, HW, generator=g)
+    dy = torch.randn(N, cout, HW, generator=g)
+    Wd, xd, dyd = W.cuda(), x.cuda(), dy.cuda()
+    st = _st()
+    if case == "fwd":
+        y = torch.full((N, cout + 5, HW), float("nan"), device="cuda")  # a channel slice of a wider buffer
+        rows = lib.ocrs_gemm_tc_batched_stat_rows(HW, N)
+        stats = torch.full((rows, 2, cout), float("nan"), device="cuda")
+        call("ocrs_gemm_tc_batched", ptr(Wd), cin, 1, cout, 0, ptr(xd), HW, 0, N * cin, cin, ptr(y), HW, (cout + 5) * HW,
+             cout, HW, cin, N, ptr(stats), st)
+        ref = torch.einsum("oi,nip->nop", W.double(), x.double())
+        assert rel_l2(y[:, :cout], ref) < 3e-6
+        assert torch.isnan(y[:, cout:]).all()
+        assert rel_l2(stats.double().sum(0)[0], ref.sum((0, 2))) < 1e-5 or ref.sum((0, 2)).abs().max() < 1e-2
+        assert rel_l2(stats.double().sum(0)[1], (ref ** 2).sum((0, 2))) < 1e-5
+    elif case == "dgrad":
+        gout = torch.empty((N, cin, HW), device="cuda")
+        call("ocrs_gemm_tc_batched", ptr(Wd), cin, 0, cout, 0, ptr(dyd), HW, 0, N * cout, cout, ptr(gout), HW, cin * HW,
+             cin, HW, cout, N, None, st)
+        assert rel_l2(gout, torch.einsum("oi,nop->nip", W.double(), dy.double())) < 3e-6
+    else:
+        part = torch.empty((N, cout, cin), device="cuda")
+        call("ocrs_gemm_tc_batched", ptr(dyd), HW, 1, N * cout, cout, ptr(xd), HW, 1, N * cin, cin, ptr(part), cin, cout * cin,
+             cout, cin, HW, N, None, st)
+        # the tensor core's truncating accumulation costs ~8e-7 per 1024 accumulated products (DESIGN section 1)
+        assert rel_l2(part.double().sum(0), torch.einsum("nop,nip->oi", dy.double(), x.double())) < 1e-6 * max(3, HW / 1024 * 1.5)
