@@ -8,7 +8,7 @@ from oracle import functional as O  # noqa: E402
 from ocrs_models_b200 import DetectionModel, balanced_cross_entropy_loss  # noqa: E402
 
 N, H, W = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (2, 96, 80)
-g = torch.Generator().manual_seed(0)
+g = torch.Generator().manual_seed(int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 torch.manual_seed(1234)
 m = DetectionModel()
 batch = {"image": torch.rand(N, 1, H, W, generator=g) - 0.5, "mask": (torch.rand(N, 1, H, W, generator=g) < 0.1).float()}
