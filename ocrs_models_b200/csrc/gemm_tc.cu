@@ -736,7 +736,10 @@ int ocrs_conv3x3_wgrad_tc(const float* dy, const float* x, int N, int H, int W, 
   OCRS_CHECK_ARG(splits >= 1, "conv3x3_wgrad_tc: bad split count");
   const long long Kl = (long long)N * H * W;
   OCRS_CHECK_ARG(Kl < 2147483647LL - 128, "conv3x3_wgrad_tc: too many pixels");
-  const int K = (int)Kl, Nn = 9 * Cin, bn = 128;
+  // N tile: 96 columns when that needs no more tiles than 128 (Cin = 32: 288 = 3 x 96 instead of 2.25 x 128: no MMA columns or
+  // B traffic wasted on padding; measured 510 -> 453 us). With more tiles (Cin = 64: 6 x 96 vs 4.5 x 128) the extra pass over
+  // the dY operand costs more than the padding (224 -> 289 us).
+  const int K = (int)Kl, Nn = 9 * Cin, bn = (ocrs_cdiv(Nn, 96) == ocrs_cdiv(Nn, 128)) ? 96 : 128;
   CUtensorMap ma, mb;
   if (make_map(&ma, dy, Cout, K, Cout, 32, TBK, true)) return -1;
   if (make_map(&mb, x, Cin, K, Cin, 32, TBK, true)) return -1;
