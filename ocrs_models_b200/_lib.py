@@ -28,6 +28,8 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_dwpw_partial_rows": [I, I, I],
     "ocrs_det_dwpw_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, P, P],
     "ocrs_det_dw3x3_fwd": [P, L, I, I, I, I, P, P, P, P, P, P],
+    "ocrs_det_activate": [P, L, I, I, L, P, P, P, P, P],
+    "ocrs_det_convt_col2im": [P, I, I, I, I, P, P, L, I, I, P],
     "ocrs_bn_finalize": [P, I, I, D, P, P, P, P, F, F, I, I, P, P, P, P, P, P],
     "ocrs_det_pool2_fwd": [P, L, I, I, I, I, P, P, P, P, L, P],
     "ocrs_det_convt_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, I, I, P],
@@ -40,6 +42,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_bnrelu_bwd_reduce": [P, L, P, L, I, I, L, P, P, P, P, P, P, P],
     "ocrs_bn_bwd_finalize": [P, I, I, D, P, P, P, P, P, P, P, P, I, P],
     "ocrs_det_dy": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, P],
+    "ocrs_det_convt_im2col": [P, L, I, I, I, I, I, I, P, P],
     "ocrs_det_pwT_bwd": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, I, P, L, P],
     "ocrs_det_pw_wgrad_workers": [I, I, I],
     "ocrs_det_pw_wgrad": [P, L, P, L, I, I, I, I, P, P, P, P, P, P, P, L, I, P, P, P, P, P, P],

@@ -865,6 +865,25 @@ plane_sum_kernel(const float* __restrict__ v, long long v_ss, int C, long long H
   if (threadIdx.x == 0) partials[((size_t)n * gridDim.x + blockIdx.x) * C + c] = a;
 }
 
+// Dcol rows (co, ky, kx) of one (sample, output channel): thread = input pixel (qy, qx), nine strided reads of dout.
+__global__ void __launch_bounds__(256)
+convt_im2col_kernel(const float* __restrict__ dout, long long dout_ss, int Cout, int Hs, int Ws, int Hin, int Win,
+                    float* __restrict__ dcol) {
+  const int qx = blockIdx.x * 32 + threadIdx.x, qy = blockIdx.y * 8 + threadIdx.y;
+  const int co = blockIdx.z % Cout, n = blockIdx.z / Cout;
+  if (qx >= Win || qy >= Hin) return;
+  const float* dp = dout + (size_t)n * dout_ss + (size_t)co * Hs * Ws;
+  const size_t HWi = (size_t)Hin * Win;
+  float* cp = dcol + ((size_t)n * Cout + co) * 9 * HWi + (size_t)qy * Win + qx;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int oy = 2 * qy + ky, ox = 2 * qx + kx;
+      cp[(size_t)(ky * 3 + kx) * HWi] = (oy < Hs && ox < Ws) ? dp[(size_t)oy * Ws + ox] : 0.f;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -914,6 +933,18 @@ int ocrs_bn_bwd_finalize(const float* partials, int nblk, int C, double count, c
   bn_bwd_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(partials, nblk, C, count, gamma, mean,
                                                               invstd, dgamma, dbeta, k1, k2, k3, training);
   OCRS_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return 0;
+}
+
+// Gradient side of ConvTranspose2d as a GEMM: Dcol[n][(co, ky, kx)][qy*Win + qx] = dout[n][co][2qy + ky][2qx + kx]
+// (0 outside the Hs x Ws crop), the operand shared by the data gradient dx[n] = W Dcol[n] and the weight gradient
+// dW = sum_n x[n] Dcol[n]^T (ocrs_gemm_tc_batched) of the levels with >= 64 input channels.
+int ocrs_det_convt_im2col(const float* dout, long long dout_ss, int N, int Cout, int Hs, int Ws, int Hin, int Win,
+                          float* dcol, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && Cout > 0 && Hin > 0 && Win > 0, "convt_im2col: bad dims");
+  dim3 block(32, 8), grid(ocrs_cdiv(Win, 32), ocrs_cdiv(Hin, 8), N * Cout);
+  convt_im2col_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dout, dout_ss, Cout, Hs, Ws, Hin, Win, dcol);
+  OCRS_CHECK_LAUNCH("convt_im2col_kernel");
   return 0;
 }
 

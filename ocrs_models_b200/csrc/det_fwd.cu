@@ -343,17 +343,132 @@ dw3x3_fwd_kernel(const float* __restrict__ x, long long x_ss, int C, int H, int 
   out[((size_t)n * C + c) * H * W + (size_t)py * W + px] = acc;
 }
 
+// Same, four consecutive pixels of a row per thread (W % 4 == 0, 16-byte aligned planes): one float4 + two scalars per
+// input row instead of twelve scalar loads.
+__global__ void __launch_bounds__(256)
+dw3x3_fwd_vec4_kernel(const float* __restrict__ x, long long x_ss, int C, int H, int W, const float* __restrict__ sc,
+                      const float* __restrict__ sh, const float* __restrict__ lo, const float* __restrict__ wdw,
+                      float* __restrict__ out) {
+  const int wq = W >> 2, idx = blockIdx.x * 256 + threadIdx.x;  // rows are short at these levels: flat (row, quad) index
+  const int py = idx / wq, px = (idx - py * wq) * 4;
+  const int c = blockIdx.y, n = blockIdx.z;
+  if (py >= H) return;
+  const float* xp = x + (size_t)n * x_ss + (size_t)c * H * W;
+  float s = 1.f, t = 0.f, l = -INFINITY;
+  if (sc) { s = sc[c]; t = sh[c]; l = lo[c]; }
+  float wk[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = wdw[(size_t)c * 9 + k];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    const float* r = xp + (size_t)yy * W + px;
+    const float4 m = *reinterpret_cast<const float4*>(r);
+    float v[6];
+    v[0] = px > 0 ? xform_apply(r[-1], s, t, l) : 0.f;
+    v[1] = xform_apply(m.x, s, t, l); v[2] = xform_apply(m.y, s, t, l);
+    v[3] = xform_apply(m.z, s, t, l); v[4] = xform_apply(m.w, s, t, l);
+    v[5] = px + 4 < W ? xform_apply(r[4], s, t, l) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) acc[q] = fmaf(v[q + kx], wk[ky * 3 + kx], acc[q]);
+  }
+  *reinterpret_cast<float4*>(out + ((size_t)n * C + c) * H * W + (size_t)py * W + px) =
+      make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose2d as a GEMM (levels with >= 64 input channels): the activated input, contiguous [N][C][HW], is the
+// B operand of Z[n] = W^T x[n] (Z rows = (co, ky, kx), ocrs_gemm_tc_batched); col2im then gathers the 1, 2 or 4 taps
+// that land on every output pixel (stride 2, 3x3: out[2qy + ky][2qx + kx] += Z[(co, ky, kx)][qy][qx]) and adds the bias.
+__global__ void __launch_bounds__(256)
+activate_kernel(const float* __restrict__ x, long long x_ss, int C, long long HW, const float* __restrict__ sc,
+                const float* __restrict__ sh, const float* __restrict__ lo, float* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+  const int c = blockIdx.y, n = blockIdx.z;
+  if (i >= HW) return;
+  const float* xp = x + (size_t)n * x_ss + (size_t)c * HW + i;
+  float* op = out + ((size_t)n * C + c) * HW + i;
+  float s = 1.f, t = 0.f, l = -INFINITY;
+  if (sc) { s = sc[c]; t = sh[c]; l = lo[c]; }
+  if (i + 4 <= HW && (((uintptr_t)xp | (uintptr_t)op) & 15) == 0) {
+    float4 v = *reinterpret_cast<const float4*>(xp);
+    v.x = xform_apply(v.x, s, t, l); v.y = xform_apply(v.y, s, t, l);
+    v.z = xform_apply(v.z, s, t, l); v.w = xform_apply(v.w, s, t, l);
+    *reinterpret_cast<float4*>(op) = v;
+  } else {
+    for (int q = 0; q < 4 && i + q < HW; ++q) op[q] = xform_apply(xp[q], s, t, l);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+convt_col2im_kernel(const float* __restrict__ Z /*[N][Cout*9][Hin*Win]*/, int Cout, int Hin, int Win,
+                    const float* __restrict__ bias, float* __restrict__ out, long long out_ss, int Hs, int Ws) {
+  const int ox = blockIdx.x * 32 + threadIdx.x, oy = blockIdx.y * 8 + threadIdx.y;
+  const int co = blockIdx.z % Cout, n = blockIdx.z / Cout;
+  if (ox >= Ws || oy >= Hs) return;
+  const size_t HWi = (size_t)Hin * Win;
+  const float* zc = Z + ((size_t)n * Cout + co) * 9 * HWi;
+  // rows: oy even -> ky = 0 from qy = oy/2 and ky = 2 from qy = oy/2 - 1; oy odd -> ky = 1 from qy = (oy-1)/2. Same for columns.
+  const int qy0 = oy >> 1, qx0 = ox >> 1;
+  const int nky = (oy & 1) ? 1 : 2, nkx = (ox & 1) ? 1 : 2;
+  float acc = bias ? bias[co] : 0.f;
+  for (int a = 0; a < nky; ++a) {
+    const int ky = (oy & 1) ? 1 : 2 * a, qy = qy0 - a;
+    if (qy < 0 || qy >= Hin) continue;
+    for (int b = 0; b < nkx; ++b) {
+      const int kx = (ox & 1) ? 1 : 2 * b, qx = qx0 - b;
+      if (qx < 0 || qx >= Win) continue;
+      acc += zc[(size_t)(ky * 3 + kx) * HWi + (size_t)qy * Win + qx];
+    }
+  }
+  out[(size_t)n * out_ss + (size_t)co * Hs * Ws + (size_t)oy * Ws + ox] = acc;
+}
+
 }  // namespace
 
 extern "C" {
+
+// a[n][c][p] = max(x * scale + shift, lo) (the producer's folded BatchNorm + ReLU) written contiguously as [N][C][HW]:
+// the activated input of ConvTranspose2d (reference models.py:76-78) as a GEMM operand.
+int ocrs_det_activate(const float* x, long long x_ss, int N, int C, long long HW, const float* sc, const float* sh,
+                      const float* lo, float* out, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && C > 0 && HW > 0, "activate: bad dims");
+  dim3 grid(ocrs_cdiv(HW, 1024), C, N);
+  activate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, C, HW, sc, sh, lo, out);
+  OCRS_CHECK_LAUNCH("activate_kernel");
+  return 0;
+}
+
+// Second half of ConvTranspose2d(k=3, stride=2) + bias as a GEMM: Z [N][Cout*9][Hin*Win] (row = (co, ky, kx), the layout
+// of the [Cin][Cout][3][3] weight read as a [Cin][9*Cout] matrix) -> out view [Cout][Hs][Ws] (crop of the 2*Hin+1 output).
+int ocrs_det_convt_col2im(const float* Z, int N, int Cout, int Hin, int Win, const float* bias, float* out,
+                          long long out_ss, int Hs, int Ws, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && Cout > 0 && Hin > 0 && Win > 0, "convt_col2im: bad dims");
+  OCRS_CHECK_ARG(Hs <= 2 * Hin + 1 && Ws <= 2 * Win + 1, "convt_col2im: crop %dx%d exceeds %dx%d", Hs, Ws, 2 * Hin + 1,
+                 2 * Win + 1);
+  dim3 block(32, 8), grid(ocrs_cdiv(Ws, 32), ocrs_cdiv(Hs, 8), N * Cout);
+  convt_col2im_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Z, Cout, Hin, Win, bias, out, out_ss, Hs, Ws);
+  OCRS_CHECK_LAUNCH("convt_col2im_kernel");
+  return 0;
+}
 
 // Depthwise 3x3 (pad 1, bias-free, reference models.py:12-17) of the activated input, written contiguously as
 // [N][C][H][W]: the B operand of ocrs_gemm_tc_batched for the 1x1 convolution of the levels with >= 64 channels.
 int ocrs_det_dw3x3_fwd(const float* x, long long x_ss, int N, int C, int H, int W, const float* sc, const float* sh,
                        const float* lo, const float* wdw, float* out, void* stream) {
   OCRS_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "dw3x3_fwd: bad dims");
-  dim3 block(32, 8), grid(ocrs_cdiv(W, 32), ocrs_cdiv(H, 8), N * C);
-  dw3x3_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, wdw, out);
+  dim3 block(32, 8);
+  if (W % 4 == 0 && x_ss % 4 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0) {
+    dim3 grid(ocrs_cdiv((long long)H * (W / 4), 256), C, N);
+    dw3x3_fwd_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, wdw, out);
+  } else {
+    dim3 grid(ocrs_cdiv(W, 32), ocrs_cdiv(H, 8), N * C);
+    dw3x3_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ss, C, H, W, sc, sh, lo, wdw, out);
+  }
   OCRS_CHECK_LAUNCH("dw3x3_fwd_kernel");
   return 0;
 }

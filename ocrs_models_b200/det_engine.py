@@ -27,7 +27,8 @@ FUSE_BN_REDUCE = os.environ.get("OCRS_DET_FUSE_BN", "1") == "1"
 # 1x1 data gradient computed inside the weight-gradient kernel for blocks with <= 16 output channels (OCRS_DET_FUSE_PWT=0: separate pass).
 FUSE_PWT = os.environ.get("OCRS_DET_FUSE_PWT", "1") == "1"
 # Levels with >= 64 channels: depthwise 3x3 as its own kernel, the 1x1 convolution and both its gradients as batched
-# tcgen05 GEMMs (csrc/gemm_tc.cu). OCRS_DET_TC=0 keeps the CUDA-core kernels there too.
+# tcgen05 GEMMs (csrc/gemm_tc.cu); ConvTranspose2d with >= 64 input channels as GEMM + col2im / im2col + GEMMs.
+# OCRS_DET_TC=0 keeps the CUDA-core kernels there too.
 USE_TC_DEEP = os.environ.get("OCRS_DET_TC", "1") == "1"
 # Keep each block's depthwise output from the forward pass for its 1x1 weight gradient (OCRS_DET_SAVE_DW=0: recompute it).
 SAVE_DW = os.environ.get("OCRS_DET_SAVE_DW", "1") == "1"
@@ -279,6 +280,44 @@ class _Plan:
         return ps
 
 
+def _convt_tc_ok(t, up: View, cout):
+    """ConvTranspose2d (models.py:76-78) as batched tcgen05 GEMMs: Z[n] = W^T x[n] with W read as [Cin][9*Cout]."""
+    HW = up.H * up.W
+    return (USE_TC_DEEP and up.C >= 64 and up.C % 32 == 0 and cout % 32 == 0 and HW % 4 == 0 and HW >= 64
+            and t.weight.data_ptr() % 16 == 0)
+
+
+def _convt_forward_tc(t, up: View, N, cout, out: View, keep, st):
+    dev = up.t.device
+    ci, HW = up.C, up.H * up.W
+    xa = torch.empty((N, ci, HW), dtype=torch.float32, device=dev)
+    call("ocrs_det_activate", up.p, up.ss, N, ci, HW, *up.xfp(), ptr(xa), st, meta=8.0 * N * HW * ci)
+    z = torch.empty((N, 9 * cout, HW), dtype=torch.float32, device=dev)
+    call("ocrs_gemm_tc_batched", ptr(t.weight), 9 * cout, 0, ci, 0, ptr(xa), HW, 0, N * ci, ci, ptr(z), HW,
+         9 * cout * HW, 9 * cout, HW, ci, N, None, st, meta=2.0 * N * HW * ci * 9 * cout)
+    call("ocrs_det_convt_col2im", ptr(z), N, cout, up.H, up.W, ptr(t.bias), out.p, out.ss, out.H, out.W, st,
+         meta=4.0 * N * (9 * cout * HW + cout * out.H * out.W))
+    return xa if keep else None
+
+
+def _convt_backward_tc(t, xa, dlo: View, N, ci, Hin, Win, st):
+    """Returns (d_up view = gradient w.r.t. the activated input, dW)."""
+    dev = xa.device
+    c, HW = dlo.C, Hin * Win
+    dcol = torch.empty((N, 9 * c, HW), dtype=torch.float32, device=dev)
+    call("ocrs_det_convt_im2col", dlo.p, dlo.ss, N, c, dlo.H, dlo.W, Hin, Win, ptr(dcol), st,
+         meta=4.0 * N * (9 * c * HW + c * dlo.H * dlo.W))
+    d_up = new_view(N, ci, Hin, Win, dev)
+    call("ocrs_gemm_tc_batched", ptr(t.weight), 9 * c, 1, ci, 0, ptr(dcol), HW, 0, N * 9 * c, 9 * c, d_up.p, HW, d_up.ss,
+         ci, HW, 9 * c, N, None, st, meta=2.0 * N * HW * ci * 9 * c)
+    wpart = torch.empty((N, ci, 9 * c), dtype=torch.float32, device=dev)
+    call("ocrs_gemm_tc_batched", ptr(xa), HW, 1, N * ci, ci, ptr(dcol), HW, 1, N * 9 * c, 9 * c, ptr(wpart), 9 * c,
+         ci * 9 * c, ci, 9 * c, HW, N, None, st, meta=2.0 * N * HW * ci * 9 * c)
+    dw = torch.empty_like(t.weight)
+    _finalize(wpart, N, ci * 9 * c, dw, st)
+    return d_up, dw
+
+
 def _identity_xf(C, dev):
     buf = torch.empty((3, C), dtype=torch.float32, device=dev)
     buf[0].fill_(1.0)
@@ -336,9 +375,13 @@ class _DetFunction(torch.autograd.Function):
             for i in reversed(range(L)):
                 t = plan.upT[i]
                 lo_half = cat_view(i, 0, d[i])
-                call("ocrs_det_convt_fwd", up.p, up.ss, N, up.C, up.H, up.W, *up.xfp(), ptr(t.weight), ptr(t.bias),
-                     d[i], lo_half.p, lo_half.ss, hs[i], ws[i], st)
-                up_inputs.append((i, up))
+                xa = None
+                if _convt_tc_ok(t, up, d[i]):
+                    xa = _convt_forward_tc(t, up, N, d[i], lo_half, save is not None, st)
+                else:
+                    call("ocrs_det_convt_fwd", up.p, up.ss, N, up.C, up.H, up.W, *up.xfp(), ptr(t.weight), ptr(t.bias),
+                         d[i], lo_half.p, lo_half.ss, hs[i], ws[i], st)
+                up_inputs.append((i, (up, xa)))
                 full = cat_view(i, 0, 2 * d[i])
                 a = plan.contract[i][0].forward(full, N, training, st, save=save)
                 up = plan.contract[i][1].forward(a, N, training, st, save=save)
@@ -404,23 +447,27 @@ class _DetFunction(torch.autograd.Function):
                 put(plan.contract[i][0].params(), gA)
                 # ConvTranspose2d
                 t = plan.upT[i]
-                up_in = up_inputs[i]
+                up_in, xa = up_inputs[i]
                 dlo = dcat[i].chan(0, c)
-                d_up = new_view(N, up_in.C, up_in.H, up_in.W, dev)
-                call("ocrs_det_convt_bwd_data", dlo.p, dlo.ss, N, c, hs[i], ws[i], ptr(t.weight), up_in.C, up_in.H,
-                     up_in.W, d_up.p, d_up.ss, st)
-                if USE_TMA and lib.ocrs_det_convt_wgrad_staged_ok(up_in.p, up_in.ss, up_in.H, up_in.W, dlo.p, dlo.ss, hs[i], ws[i]):
-                    workers = lib.ocrs_det_convt_wgrad_staged_workers(N, up_in.H, up_in.W, up_in.C, c)
-                    wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
-                    call("ocrs_det_convt_wgrad_staged", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
-                         dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
+                if xa is not None:  # >= 64 input channels: im2col + two batched tcgen05 GEMMs
+                    d_up, dw = _convt_backward_tc(t, xa, dlo, N, up_in.C, up_in.H, up_in.W, st)
+                    xa = None
                 else:
-                    workers = lib.ocrs_det_convt_wgrad_workers(N, up_in.H, up_in.W)
-                    wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
-                    call("ocrs_det_convt_wgrad", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
-                         dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
-                dw = torch.empty_like(t.weight)
-                _finalize(wpart, workers, t.weight.numel(), dw, st)
+                    d_up = new_view(N, up_in.C, up_in.H, up_in.W, dev)
+                    call("ocrs_det_convt_bwd_data", dlo.p, dlo.ss, N, c, hs[i], ws[i], ptr(t.weight), up_in.C, up_in.H,
+                         up_in.W, d_up.p, d_up.ss, st)
+                    if USE_TMA and lib.ocrs_det_convt_wgrad_staged_ok(up_in.p, up_in.ss, up_in.H, up_in.W, dlo.p, dlo.ss, hs[i], ws[i]):
+                        workers = lib.ocrs_det_convt_wgrad_staged_workers(N, up_in.H, up_in.W, up_in.C, c)
+                        wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
+                        call("ocrs_det_convt_wgrad_staged", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(),
+                             dlo.p, dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
+                    else:
+                        workers = lib.ocrs_det_convt_wgrad_workers(N, up_in.H, up_in.W)
+                        wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
+                        call("ocrs_det_convt_wgrad", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
+                             dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
+                    dw = torch.empty_like(t.weight)
+                    _finalize(wpart, workers, t.weight.numel(), dw, st)
                 brows = lib.ocrs_reduce_rows(N, hs[i] * ws[i])
                 bpart = torch.empty((brows, c), dtype=torch.float32, device=dev)
                 call("ocrs_plane_sum", dlo.p, dlo.ss, N, c, hs[i] * ws[i], ptr(bpart), st)

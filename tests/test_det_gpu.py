@@ -275,6 +275,42 @@ def test_convt_fwd_bwd(N, cin, cout, h, w, Hs, Ws):
     assert rel_l2(db, b.grad) < 1e-5
 
 
+@pytest.mark.parametrize("N,cin,cout,h,w,Hs,Ws", [(2, 64, 32, 8, 8, 16, 16), (1, 256, 128, 8, 12, 17, 25), (3, 128, 64, 10, 10, 20, 21),
+                                                  (2, 64, 32, 16, 4, 33, 8)])
+def test_convt_as_tcgen05_gemms(N, cin, cout, h, w, Hs, Ws):
+    """ConvTranspose2d with >= 64 input channels: activate -> batched GEMM -> col2im, im2col -> two batched GEMMs
+    (det_engine._convt_forward_tc / _convt_backward_tc) vs fp64 conv_transpose2d (models.py:76-89, incl. the crop)."""
+    from ocrs_models_b200 import det_engine as E
+
+    g = torch.Generator().manual_seed(cin + h)
+    x = torch.randn(N, cin, h, w, generator=g)
+    xf = _rand_xf(cin, g)
+    wt = (torch.randn(cin, cout, 3, 3, generator=g) * 0.1).double().requires_grad_(True)
+    b = torch.randn(cout, generator=g).double().requires_grad_(True)
+    a = _apply_xf(x, xf).double().requires_grad_(True)
+    ref = F.conv_transpose2d(a, wt, b, stride=2)[:, :, :Hs, :Ws]
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout.double())
+    t = torch.nn.ConvTranspose2d(cin, cout, 3, stride=2).cuda()
+    with torch.no_grad():
+        t.weight.copy_(wt.detach().float())
+        t.bias.copy_(b.detach().float())
+    up = E.View(x.cuda(), 0, cin * h * w, cin, h, w, tuple(v.cuda() for v in xf))
+    assert E._convt_tc_ok(t, up, cout)
+    cat = torch.zeros(N, cout + 3, Hs, Ws, device="cuda")
+    out = E.View(cat, 0, (cout + 3) * Hs * Ws, cout, Hs, Ws)
+    xa = E._convt_forward_tc(t, up, N, cout, out, True, _stream())
+    assert rel_l2(xa.view(N, cin, h, w), a.detach()) < 1e-6
+    assert rel_l2(cat[:, :cout], ref) < 2e-6
+    assert cat[:, cout:].abs().max().item() == 0
+    dcat = torch.zeros_like(cat)
+    dcat[:, :cout] = dout.cuda()
+    dlo = E.View(dcat, 0, (cout + 3) * Hs * Ws, cout, Hs, Ws)
+    d_up, dw = E._convt_backward_tc(t, xa, dlo, N, cin, h, w, _stream())
+    assert rel_l2(d_up.t, a.grad) < 2e-6
+    assert rel_l2(dw, wt.grad) < 2e-6
+
+
 def _loss_case(p, t):
     from ocrs_models_b200 import balanced_cross_entropy_loss
 
