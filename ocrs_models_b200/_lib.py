@@ -30,7 +30,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_dw3x3_fwd": [P, L, I, I, I, I, P, P, P, P, P, P],
     "ocrs_det_activate": [P, L, I, I, L, P, P, P, P, P],
     "ocrs_det_convt_col2im": [P, I, I, I, I, P, P, L, I, I, P],
-    "ocrs_bn_finalize": [P, I, I, D, P, P, P, P, F, F, I, I, P, P, P, P, P, P],
+    "ocrs_bn_finalize": [P, I, I, D, P, P, P, P, F, F, I, I, P, P, P, P, P, P, P],
     "ocrs_det_pool2_fwd": [P, L, I, I, I, I, P, P, P, P, L, P],
     "ocrs_det_convt_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, I, I, P],
     "ocrs_det_outconv_fwd": [P, L, I, I, I, I, P, P, P, P, P, P, P],
@@ -112,6 +112,11 @@ SIGNATURES: dict[str, list] = {
     # eval-path post-processing (csrc/postprocess.cu)
     "ocrs_cc_label": [P, F, I, I, I, P, P, P, P],
     "ocrs_cc_boundary": [P, I, I, I, P, I, P, P],
+    # multi-tensor step glue (csrc/glue.cu)
+    "ocrs_grad_deliver_max": [],
+    "ocrs_weight_prep_max": [],
+    "ocrs_grad_deliver": [P, P, P, P, P, P, P, P, P, I, P],
+    "ocrs_weight_prep": [P, P, P, P, P, P, P, P, P, P, P, I, P],
     # optimiser glue (csrc/optim.cu)
     "ocrs_optim_blocks": [],
     "ocrs_grad_norm": [P, L, F, P, P, P],

@@ -165,9 +165,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk,
                                    float* running_var, float momentum, float eps, int training,
                                    int relu, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ lo, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out) {
+                                   float* __restrict__ invstd_out, long long* num_batches_tracked) {
   __shared__ double red[2][32];
   const int c = blockIdx.x;
+  if (training && num_batches_tracked && c == 0 && threadIdx.x == 0) num_batches_tracked[0] += 1;
   double mean, var;
   if (training) {
     double a = 0.0, b = 0.0;
@@ -498,14 +499,17 @@ int ocrs_det_dwpw_fwd(const float* x, long long x_ss, int N, int Cin, int H, int
   return 0;
 }
 
+// BatchNorm2d statistics from (sum, sum of squares) partial rows -> the consumers' folded (scale, shift, lo) transform,
+// mean / invstd for the backward pass, running statistics and (training, optional) num_batches_tracked += 1
+// (reference models.py:18-20: nn.BatchNorm2d in train or eval mode).
 int ocrs_bn_finalize(const float* partials, int nblk, int C, double count, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum,
                      float eps, int training, int relu, float* scale, float* shift, float* lo,
-                     float* mean_out, float* invstd_out, void* stream) {
+                     float* mean_out, float* invstd_out, long long* num_batches_tracked, void* stream) {
   OCRS_CHECK_ARG(C > 0, "bn_finalize: bad channel count");
   bn_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(
       partials, nblk, C, count, gamma, beta, running_mean, running_var, momentum, eps, training,
-      relu, scale, shift, lo, mean_out, invstd_out);
+      relu, scale, shift, lo, mean_out, invstd_out, num_batches_tracked);
   OCRS_CHECK_LAUNCH("bn_finalize_kernel");
   return 0;
 }

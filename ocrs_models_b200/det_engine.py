@@ -16,6 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr
+from .grads import Partial, deliver
 
 NEG_INF = float("-inf")
 # TMA-pipelined DepthwiseConv kernels (csrc/det_tma.cu) wherever the views are TMA-addressable; OCRS_DET_TMA=0 keeps the
@@ -113,9 +114,8 @@ class _Sep:
         bn = self.bn
         call("ocrs_bn_finalize", ptr(partials), rows, self.cout, float(N * H * W), ptr(bn.weight), ptr(bn.bias),
              ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, int(training), 1,
-             xf_dst[0].data_ptr(), xf_dst[1].data_ptr(), xf_dst[2].data_ptr(), ptr(stats[0]), ptr(stats[1]), st)
-        if training:
-            bn.num_batches_tracked.add_(1)
+             xf_dst[0].data_ptr(), xf_dst[1].data_ptr(), xf_dst[2].data_ptr(), ptr(stats[0]), ptr(stats[1]),
+             ptr(bn.num_batches_tracked), st)
         y.xf = xf_dst
         if save is not None:
             save[id(self)] = (inp, y, stats, bool(training), dwo)
@@ -146,9 +146,8 @@ class _Sep:
         bn = self.bn
         call("ocrs_bn_finalize", ptr(partials), rows, co, float(N * HW), ptr(bn.weight), ptr(bn.bias),
              ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, int(training), 1,
-             xf_dst[0].data_ptr(), xf_dst[1].data_ptr(), xf_dst[2].data_ptr(), ptr(stats[0]), ptr(stats[1]), st)
-        if training:
-            bn.num_batches_tracked.add_(1)
+             xf_dst[0].data_ptr(), xf_dst[1].data_ptr(), xf_dst[2].data_ptr(), ptr(stats[0]), ptr(stats[1]),
+             ptr(bn.num_batches_tracked), st)
         y.xf = xf_dst
         if save is not None:
             save[id(self)] = (inp, y, stats, bool(training), ("tc", dwo))
@@ -166,9 +165,7 @@ class _Sep:
         wpart = torch.empty((N, co, ci), dtype=torch.float32, device=dev)
         call("ocrs_gemm_tc_batched", ptr(dy), HW, 1, N * co, co, ptr(dwo), HW, 1, N * ci, ci, ptr(wpart), ci, co * ci,
              co, ci, HW, N, None, st, meta=2.0 * N * HW * ci * co)
-        d_wpw = torch.empty_like(self.pw.weight)
-        _finalize(wpart, N, co * ci, d_wpw, st)
-        return g, d_wpw
+        return g, Partial(wpart, N, co * ci)
 
     def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False, bn_pending=None):
         """d_a: gradient w.r.t. this block's activated output. Writes the gradient w.r.t. the
@@ -218,12 +215,10 @@ class _Sep:
                 wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
                 call("ocrs_det_pw_wgrad", d_a.p, d_a.ss, y.p, y.ss, N, co, H, W, *k, inp.p, inp.ss, ci, *inp.xfp(),
                      ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
-            d_wpw = torch.empty_like(self.pw.weight)
-            _finalize(wpart, workers, co * ci, d_wpw, st)
+            d_wpw = Partial(wpart, workers, co * ci)
         dwo = None
         if dx is None:
             dx = new_view(N, ci, H, W, dev)
-        d_wdw = torch.empty_like(self.dw.weight)
         if USE_TMA and lib.ocrs_det_tma_supported(g.p, g.ss, inp.p, inp.ss, H, W) and lib.ocrs_det_tma_supported(dx.p, dx.ss, dx.p, dx.ss, H, W):
             drows = lib.ocrs_det_sep_dw_bwd_rows(N, H, W, ci)
             dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
@@ -243,8 +238,8 @@ class _Sep:
             dpart = torch.empty((drows, ci, 9), dtype=torch.float32, device=dev)
             call("ocrs_det_dw_bwd", g.p, g.ss, inp.p, inp.ss, N, ci, H, W, *inp.xfp(), ptr(self.dw.weight), dx.p,
                  dx.ss, int(accumulate), ptr(dpart), st, meta=4.0 * N * HW * 3 * ci)
-        _finalize(dpart, drows, ci * 9, d_wdw, st)
-        return [d_wdw, d_wpw, coef[0].clone(), coef[1].clone()], dx
+        # weight gradients stay partial rows; grads.deliver reduces all of the step's in one launch
+        return [Partial(dpart, drows, ci * 9), d_wpw, coef[0], coef[1]], dx
 
 
 class _Plan:
@@ -313,17 +308,23 @@ def _convt_backward_tc(t, xa, dlo: View, N, ci, Hin, Win, st):
     wpart = torch.empty((N, ci, 9 * c), dtype=torch.float32, device=dev)
     call("ocrs_gemm_tc_batched", ptr(xa), HW, 1, N * ci, ci, ptr(dcol), HW, 1, N * 9 * c, 9 * c, ptr(wpart), 9 * c,
          ci * 9 * c, ci, 9 * c, HW, N, None, st, meta=2.0 * N * HW * ci * 9 * c)
-    dw = torch.empty_like(t.weight)
-    _finalize(wpart, N, ci * 9 * c, dw, st)
-    return d_up, dw
+    return d_up, Partial(wpart, N, ci * 9 * c)
+
+
+_IDENT: dict = {}
 
 
 def _identity_xf(C, dev):
-    buf = torch.empty((3, C), dtype=torch.float32, device=dev)
-    buf[0].fill_(1.0)
-    buf[1].zero_()
-    buf[2].fill_(NEG_INF)
-    return (buf[0], buf[1], buf[2])
+    """(scale, shift, lo) = (1, 0, -inf): constants, built once per (channels, device)."""
+    key = (C, dev)
+    xf = _IDENT.get(key)
+    if xf is None:
+        buf = torch.empty((3, C), dtype=torch.float32, device=dev)
+        buf[0].fill_(1.0)
+        buf[1].zero_()
+        buf[2].fill_(NEG_INF)
+        xf = _IDENT[key] = (buf[0], buf[1], buf[2])
+    return xf
 
 
 class _DetFunction(torch.autograd.Function):
@@ -347,7 +348,12 @@ class _DetFunction(torch.autograd.Function):
             raise RuntimeError(f"DetectionModel needs inputs of at least {2**L}x{2**L}, got {H}x{W}")
         # concat buffers of the six Up stages: [ConvT output | skip]
         cat = [torch.empty((N, 2 * d[i], hs[i], ws[i]), dtype=torch.float32, device=dev) for i in range(L)]
-        catxf = [_identity_xf(2 * d[i], dev) for i in range(L)]
+        # their load transforms: identity for the ConvT half, the skip producer's BatchNorm+ReLU (written by its
+        # bn_finalize) for the other half - per forward pass, one copy of the constant identity rows for all six
+        ident = _identity_xf(2 * sum(d[:L]), dev)
+        xfbuf = torch.stack(ident)
+        coff = [2 * sum(d[:i]) for i in range(L + 1)]
+        catxf = [tuple(xfbuf[r, coff[i] : coff[i + 1]] for r in range(3)) for i in range(L)]
 
         def cat_view(i, lo, hi):
             xf = tuple(a[lo:hi] for a in catxf[i])
@@ -432,9 +438,8 @@ class _DetFunction(torch.autograd.Function):
                 part = torch.empty((rows, d[0] + 1), dtype=torch.float32, device=dev)
                 call("ocrs_det_outconv_bwd", ptr(dprob), ptr(prob), last.p, last.ss, N, d[0], H, W, *last.xfp(),
                      ptr(plan.out.weight), d_a.p, d_a.ss, ptr(part), st)
-            wb = torch.empty((d[0] + 1,), dtype=torch.float32, device=dev)
-            _finalize(part, rows, d[0] + 1, wb, st)
-            put([plan.out.weight, plan.out.bias], [wb[: d[0]].reshape(1, d[0], 1, 1).clone(), wb[d[0] :].clone()])
+            put([plan.out.weight, plan.out.bias],
+                [Partial(part, rows, d[0], ld=d[0] + 1), Partial(part, rows, 1, ld=d[0] + 1, off=d[0])])
 
             dcat = [None] * L
             # up path, in reverse of forward order: up[0] first
@@ -466,14 +471,11 @@ class _DetFunction(torch.autograd.Function):
                         wpart = torch.empty((workers,) + tuple(t.weight.shape), dtype=torch.float32, device=dev)
                         call("ocrs_det_convt_wgrad", up_in.p, up_in.ss, N, up_in.C, up_in.H, up_in.W, *up_in.xfp(), dlo.p,
                              dlo.ss, c, hs[i], ws[i], ptr(wpart), st)
-                    dw = torch.empty_like(t.weight)
-                    _finalize(wpart, workers, t.weight.numel(), dw, st)
+                    dw = Partial(wpart, workers, t.weight.numel())
                 brows = lib.ocrs_reduce_rows(N, hs[i] * ws[i])
                 bpart = torch.empty((brows, c), dtype=torch.float32, device=dev)
                 call("ocrs_plane_sum", dlo.p, dlo.ss, N, c, hs[i] * ws[i], ptr(bpart), st)
-                db = torch.empty_like(t.bias)
-                _finalize(bpart, brows, c, db, st)
-                put([t.weight, t.bias], [dw, db])
+                put([t.weight, t.bias], [dw, Partial(bpart, brows, c)])
                 d_a = d_up  # gradient w.r.t. the activated input of this ConvT
             # d_a now = gradient w.r.t. x_down[L-1] (pooled, activated)
             d_pooled = d_a
@@ -503,8 +505,9 @@ class _DetFunction(torch.autograd.Function):
             put(plan.in_conv[1].params(), gB)
             gA, dx = plan.in_conv[0].backward(recs, d_mid, N, st, None, bn_pending=pend)
             put(plan.in_conv[0].params(), gA)
+            param_grads = deliver(plan.all_params(), grads, st)
         dxt = dx.t if ctx.needs_input_grad[1] else None
-        out = [None, dxt] + [grads.get(id(p)) for p in plan.all_params()]
+        out = [None, dxt] + param_grads
         ctx.acts = None
         return tuple(out)
 

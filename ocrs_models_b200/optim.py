@@ -52,6 +52,9 @@ class FusedAdam:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_g[o : o + p.numel()].view_as(p)
+                # the backward passes of this package accumulate straight into this view (grads.deliver) instead of
+                # handing autograd one tensor per parameter to add
+                p._ocrs_grad_sink = p.grad
         self.params, self.n = params, total
         self.lr, self.betas, self.eps = lr, betas, eps
         self.max_grad_norm = max_grad_norm

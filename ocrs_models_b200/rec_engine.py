@@ -14,6 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr
+from .grads import Partial, deliver
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -54,9 +55,13 @@ _PRECISION = "parity"
 class Split:
     """A weight matrix split for the 3xTF32 GEMM: `hi` (TF32-exact) and `lo` (remainder), same layout."""
 
-    __slots__ = ("hi", "lo")
+    __slots__ = ("hi", "lo", "src")
 
-    def __init__(self, w, st):
+    def __init__(self, w, st, halves=None):
+        self.src = w  # the unsplit matrix in the same layout (None if there is none), for GEMMs that cannot use the halves
+        if halves is not None:  # already produced (ocrs_weight_prep)
+            self.hi, self.lo = halves
+            return
         w = w.detach().contiguous()
         self.hi = torch.empty_like(w)
         self.lo = torch.empty_like(w)
@@ -83,7 +88,7 @@ def conv3x3(x, N, H, W, cin, wp, cout, st, bias=None, relu=False, stats=None):
 
 
 def conv3x3_wgrad(dy, x, N, H, W, cin, cout, st):
-    """[cout, (ky, kx, ci)] weight gradient of conv3x3 from dy [N*H*W, cout] and the NHWC input x."""
+    """[cout, (ky, kx, ci)] weight gradient of conv3x3 from dy [N*H*W, cout] and the NHWC input x, as split-K partial rows."""
     lib = _lib.lib()
     K = N * H * W
     tiles = ((9 * cin + 127) // 128) * ((cout + 127) // 128)
@@ -92,11 +97,7 @@ def conv3x3_wgrad(dy, x, N, H, W, cin, cout, st):
     part = _empty((splits, cout, 9 * cin), x.device)
     call("ocrs_conv3x3_wgrad_tc", ptr(dy), ptr(x), N, H, W, cin, cout, ptr(part), splits, st,
          meta=2.0 * K * cout * 9 * cin)
-    if splits == 1:
-        return part[0]
-    out = _empty((cout, 9 * cin), x.device)
-    call("ocrs_finalize_partials", ptr(part), splits, cout * 9 * cin, ptr(out), st)
-    return out
+    return Partial(part, splits, cout * 9 * cin, conv=(cin, 9))  # split-K rows, reduced + re-laid out by grads.deliver
 
 
 def _implicit_ok(cin, kh):
@@ -108,17 +109,19 @@ def _empty(shape, dev):
 
 
 def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bias=None, relu=False,
-         accumulate=False, stats=None, split_ok=False, exact=False, b_weight=False):
+         accumulate=False, stats=None, split_ok=False, exact=False, b_weight=False, lazy=None):
     """C[M,N] = op(A) op(B). A/B are tensors or raw pointers. With `split_ok` the reduction is split
     over K when the output has too few tiles to fill the GPU. `exact` forces the fp32-FMA kernel:
     outputs that feed ReLU / max-pool decisions must be accurate to ~1e-6, because a perturbation d
     of a pre-activation flips a fraction ~d of the gates and moves gradients by ~sqrt(d). Kept as
-    an A/B switch: the 4-accumulator 3xTF32 tensor-core kernel reaches the same accuracy."""
+    an A/B switch: the 4-accumulator 3xTF32 tensor-core kernel reaches the same accuracy.
+    `lazy` (a dict of Partial keyword arguments, with `split_ok`): the result is a parameter gradient - return the split-K
+    rows as a grads.Partial instead of reducing them here."""
     dev = out.device if out is not None else (A.device if isinstance(A, torch.Tensor) else None)
     pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
-    b_lo = None
+    b_lo = b_src = None
     if isinstance(B, Split):
-        b_lo, B = B.lo, B.hi
+        b_lo, b_src, B = B.lo, B.src, B.hi
     pb = B.data_ptr() if isinstance(B, torch.Tensor) else B
     if out is None:
         out = _empty((M, N), dev)
@@ -126,6 +129,8 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bi
         ldc = N
     lib = _lib.lib()
     tc = GEMM_BACKEND == "tc" and not exact and bool(lib.ocrs_gemm_tc_supported(pa, lda, pb, ldb))
+    if b_lo is not None and not tc and b_src is not None:  # e.g. lda = 97 (the linear head's data gradient): fp32 GEMM on the unsplit matrix
+        pb, b_lo = b_src.data_ptr(), None
     fn = "ocrs_gemm_tc" if tc else "ocrs_gemm"
     splits = 1
     if split_ok:
@@ -149,7 +154,12 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, st, out=None, ldc=None, bi
         part = _empty((splits, M, N), out.device)
         call(fn, pa, lda, int(a_kmajor), pb, ldb, int(b_kmajor), ptr(part), N, M, N, K, None, 0, 0, None,
              splits, st, meta=2.0 * M * N * K)
+        if lazy is not None:
+            return Partial(part, splits, M * N, **lazy)
         call("ocrs_finalize_partials", ptr(part), splits, M * N, ptr(out), st)
+    if lazy is not None:
+        assert ldc == N
+        return Partial(out, 1, M * N, **lazy)
     return out
 
 
@@ -159,9 +169,7 @@ def colsum(A, lda, M, N, st, dev):
     part = _empty((rows, N), dev)
     pa = A.data_ptr() if isinstance(A, torch.Tensor) else A
     call("ocrs_colsum", pa, lda, M, N, ptr(part), st)
-    out = _empty((N,), dev)
-    call("ocrs_finalize_partials", ptr(part), rows, N, ptr(out), st)
-    return out
+    return Partial(part, rows, N)
 
 
 def im2col(x, N, H, W, C, kh, kw, ph, pw, st):
@@ -172,7 +180,8 @@ def im2col(x, N, H, W, C, kh, kw, ph, pw, st):
 
 
 def _w_fwd(w):
-    """[Cout, Cin, kh, kw] -> [Cout, (ky, kx, ci)] matching the im2col column order."""
+    """[Cout, Cin, kh, kw] -> [Cout, (ky, kx, ci)] matching the im2col column order (layout reference for the tests; the
+    step builds it with ocrs_weight_prep)."""
     return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
@@ -181,10 +190,49 @@ def _w_dgrad(w):
     return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous()
 
 
-def _w_grad_back(dwp, w):
-    """[Cout, (ky, kx, ci)] -> parameter layout [Cout, Cin, kh, kw]."""
-    co, ci, kh, kw = w.shape
-    return dwp.reshape(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+def prepare_weights(model, st, dev, backward: bool):
+    """Every per-step weight operand of the GEMMs in ONE launch (csrc/glue.cu ocrs_weight_prep): convolution weights
+    re-laid out for the implicit GEMM (forward [Cout][(ky,kx,ci)]; flipped [Cin][(ky,kx,co)] for the data gradient),
+    all GEMM weights split into TF32 hi/lo, W_hh transposed for the GRU backward. Returns dicts keyed by id(parameter):
+    fwd / dg (convolutions), w (GRU input projections, linear head), whhT."""
+    import ctypes
+
+    split = PRESPLIT and GEMM_BACKEND == "tc"
+    split_conv = split and not EXACT_FWD
+    ent, prep = [], dict(fwd={}, dg={}, w={}, whhT={})
+
+    def pair(shape, want):
+        hi = _empty(shape, dev)
+        return hi, (_empty(shape, dev) if want else None)
+
+    for name in ("3", "7", "9", "13", "15", "19"):
+        w = model.conv[name].weight
+        co, ci, kh, kw = w.shape
+        hi, lo = pair((co, kh * kw * ci), split_conv)
+        dhi, dlo = pair((ci, kh * kw * co), split_conv) if backward else (None, None)
+        ent.append((ptr(w), ptr(hi), ptr(lo), ptr(dhi), ptr(dlo), w.numel(), 1, co, ci, kh, kw))
+        prep["fwd"][id(w)] = Split(None, st, (hi, lo)) if lo is not None else hi
+        if backward:
+            prep["dg"][id(w)] = Split(None, st, (dhi, dlo)) if dlo is not None else dhi
+    if split:
+        ws = [getattr(model.gru, f"weight_ih_l{l}{sfx}") for l in range(2) for sfx in ("", "_reverse")] + [model.output[0].weight]
+        for w in ws:
+            hi, lo = pair(tuple(w.shape), True)
+            ent.append((ptr(w), ptr(hi), ptr(lo), None, None, w.numel(), 0, 0, 0, 0, 0))
+            prep["w"][id(w)] = Split(w, st, (hi, lo))
+    if backward:
+        for l in range(2):
+            for sfx in ("", "_reverse"):
+                w = getattr(model.gru, f"weight_hh_l{l}{sfx}")
+                t_ = _empty((w.shape[1], w.shape[0]), dev)
+                ent.append((ptr(w), ptr(t_), None, None, None, w.numel(), 2, w.shape[0], w.shape[1], 0, 0))
+                prep["whhT"][id(w)] = t_
+    n = len(ent)
+    cols = list(zip(*ent))
+    ptrs = [(ctypes.c_void_p * n)(*c) for c in cols[:5]]
+    ints = [(ctypes.c_int * n)(*c) for c in cols[5:]]
+    call("ocrs_weight_prep", *ptrs, *ints, n, st)
+    return prep
 
 
 class _BNState:
@@ -214,9 +262,7 @@ def _bn_finalize(bn, stats, rows, count, training, relu, st, dev):
     C = bn.num_features
     call("ocrs_bn_finalize", ptr(stats), rows, C, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
          ptr(bn.running_var), BN_MOMENTUM, BN_EPS, int(training), int(relu), ptr(s.buf[0]), ptr(s.buf[1]),
-         ptr(s.buf[2]), ptr(s.buf[3]), ptr(s.buf[4]), st)
-    if training:
-        bn.num_batches_tracked.add_(1)
+         ptr(s.buf[2]), ptr(s.buf[3]), ptr(s.buf[4]), ptr(bn.num_batches_tracked), st)
     return s
 
 
@@ -232,6 +278,8 @@ class _RecFunction(torch.autograd.Function):
         save = any(ctx.needs_input_grad)
         rec = {}
         with torch.cuda.device(dev):
+            wprep = prepare_weights(model, st, dev, save)
+            wfwd, wsplit = wprep["fwd"], wprep["w"]
             # conv.0 + ReLU + MaxPool2 -> NHWC [N, H/2, W/2, 32]
             H1, W1 = H // 2, W // 2
             a0 = _empty((N, H1, W1, 32), dev)
@@ -244,13 +292,13 @@ class _RecFunction(torch.autograd.Function):
                     M = N * Ho * Wo
                     rows = lib.ocrs_gemm_stat_rows(M)
                     stats = _empty((rows, 2, cout), dev) if training else None
-                    y = conv3x3(inp, N, Hh, Ww, cin, _w_fwd(conv.weight), cout, st, stats=stats)
+                    y = conv3x3(inp, N, Hh, Ww, cin, wfwd[id(conv.weight)], cout, st, stats=stats)
                 else:
                     col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, kh, kh, pad, pad, st)
                     M = N * Ho * Wo
                     rows = lib.ocrs_gemm_stat_rows(M)
                     stats = _empty((rows, 2, cout), dev) if training else None
-                    y = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, cout, col.shape[1],
+                    y = gemm(col, col.shape[1], True, wfwd[id(conv.weight)], col.shape[1], True, M, cout, col.shape[1],
                              st, stats=stats, exact=EXACT_FWD, b_weight=True)
                 bs = _bn_finalize(bn, stats, rows, M, training, relu, st, dev)
                 Hp, Wp = Ho // ph, Wo // pw
@@ -264,11 +312,11 @@ class _RecFunction(torch.autograd.Function):
 
             def conv_bias_relu(inp, Hh, Ww, cin, conv):
                 if _implicit_ok(cin, 3):
-                    a = conv3x3(inp, N, Hh, Ww, cin, _w_fwd(conv.weight), conv.out_channels, st, bias=conv.bias, relu=True)
+                    a = conv3x3(inp, N, Hh, Ww, cin, wfwd[id(conv.weight)], conv.out_channels, st, bias=conv.bias, relu=True)
                     return a, dict(col=None, inp=inp, a=a, inp_geom=(Hh, Ww, cin))
                 col, Ho, Wo = im2col(inp, N, Hh, Ww, cin, 3, 3, 1, 1, st)
                 M = N * Ho * Wo
-                a = gemm(col, col.shape[1], True, _w_fwd(conv.weight), col.shape[1], True, M, conv.out_channels,
+                a = gemm(col, col.shape[1], True, wfwd[id(conv.weight)], col.shape[1], True, M, conv.out_channels,
                          col.shape[1], st, bias=conv.bias, relu=True, exact=EXACT_FWD, b_weight=True)
                 return a, dict(col=col, inp=inp, a=a, inp_geom=(Hh, Ww, cin))
 
@@ -295,7 +343,7 @@ class _RecFunction(torch.autograd.Function):
                 for sfx in ("", "_reverse"):
                     w_ih = getattr(gru, f"weight_ih_l{layer}{sfx}")
                     b_ih = getattr(gru, f"bias_ih_l{layer}{sfx}")
-                    gi.append(gemm(layer_in, isz, True, w_ih, isz, True, TN, 768, isz, st, bias=b_ih, b_weight=True))
+                    gi.append(gemm(layer_in, isz, True, wsplit.get(id(w_ih), w_ih), isz, True, TN, 768, isz, st, bias=b_ih, b_weight=True))
                 out = _empty((T, N, 512), dev)
                 gates = _empty((T, N, 2, 4, 256), dev)
                 call("ocrs_gru_layer_fwd_persist", ptr(gi[0]), ptr(gi[1]), ptr(getattr(gru, f"weight_hh_l{layer}")),
@@ -305,7 +353,7 @@ class _RecFunction(torch.autograd.Function):
                 layer_in = out
             lin = model.output[0]
             C = lin.out_features
-            logits = gemm(layer_in, 512, True, lin.weight, 512, True, TN, C, 512, st, bias=lin.bias, b_weight=True)
+            logits = gemm(layer_in, 512, True, wsplit.get(id(lin.weight), lin.weight), 512, True, TN, C, 512, st, bias=lin.bias, b_weight=True)
             lp = _empty((T, N, C), dev)
             call("ocrs_log_softmax_fwd", ptr(logits), ptr(lp), TN, C, st)
         if save:
@@ -313,6 +361,7 @@ class _RecFunction(torch.autograd.Function):
             ctx.rec = rec
             ctx.gru_rec = gru_rec
             ctx.misc = (x, a0, lp, N, H, W, T, C, bool(training))
+            ctx.wprep = wprep
         return lp
 
     @staticmethod
@@ -320,6 +369,7 @@ class _RecFunction(torch.autograd.Function):
         model = ctx.model
         rec, gru_rec = ctx.rec, ctx.gru_rec
         x, a0, lp, N, H, W, T, C, training = ctx.misc
+        wdg, wsplit, whhT_of = ctx.wprep["dg"], ctx.wprep["w"], ctx.wprep["whhT"]
         dev = lp.device
         st = _lib.stream_ptr(dev)
         lib = _lib.lib()
@@ -331,18 +381,14 @@ class _RecFunction(torch.autograd.Function):
             dlog = _empty((TN, C), dev)
             call("ocrs_log_softmax_bwd", ptr(lp), ptr(g_lp), ptr(dlog), TN, C, st)
             out1 = gru_rec[1]["out"]
-            grads[id(lin.weight)] = gemm(dlog, C, False, out1, 512, False, C, 512, TN, st, split_ok=True)
+            grads[id(lin.weight)] = gemm(dlog, C, False, out1, 512, False, C, 512, TN, st, split_ok=True, lazy={})
             grads[id(lin.bias)] = colsum(dlog, C, TN, C, st, dev)
-            d_out = gemm(dlog, C, True, lin.weight, 512, False, TN, 512, C, st, b_weight=True)
+            d_out = gemm(dlog, C, True, wsplit.get(id(lin.weight), lin.weight), 512, False, TN, 512, C, st, b_weight=True)
             for layer in (1, 0):
                 r = gru_rec[layer]
                 isz, xin, out, gates = r["isz"], r["x"], r["out"], r["gates"]
                 names = [f"l{layer}", f"l{layer}_reverse"]
-                whhT = []
-                for nm in names:
-                    t_ = _empty((256, 768), dev)
-                    call("ocrs_transpose", ptr(getattr(gru, "weight_hh_" + nm)), ptr(t_), 768, 256, st)
-                    whhT.append(t_)
+                whhT = [whhT_of[id(getattr(gru, "weight_hh_" + nm))] for nm in names]
                 dgi = [_empty((TN, 768), dev) for _ in range(2)]
                 dgh = [_empty((TN, 768), dev) for _ in range(2)]
                 call("ocrs_gru_layer_bwd_persist", ptr(whhT[0]), ptr(whhT[1]), ptr(d_out), ptr(out), ptr(gates),
@@ -350,7 +396,7 @@ class _RecFunction(torch.autograd.Function):
                 d_in = _empty((TN, isz), dev)
                 for d, nm in enumerate(names):
                     w_ih = getattr(gru, "weight_ih_" + nm)
-                    grads[id(w_ih)] = gemm(dgi[d], 768, False, xin, isz, False, 768, isz, TN, st, split_ok=True)
+                    grads[id(w_ih)] = gemm(dgi[d], 768, False, xin, isz, False, 768, isz, TN, st, split_ok=True, lazy={})
                     grads[id(getattr(gru, "bias_ih_" + nm))] = colsum(dgi[d], 768, TN, 768, st, dev)
                     grads[id(getattr(gru, "bias_hh_" + nm))] = colsum(dgh[d], 768, TN, 768, st, dev)
                     # dW_hh = sum_t dgh[t]^T h_prev[t]; h_prev[t] = out[t-1] (fwd) / out[t+1] (reverse)
@@ -362,12 +408,12 @@ class _RecFunction(torch.autograd.Function):
                         else:
                             pa = dgh[d].data_ptr()
                             pb = out.data_ptr() + 4 * (N * 512 + 256)
-                        dwhh = _empty((768, 256), dev)
-                        gemm(pa, 768, False, pb, 512, False, 768, 256, rows, st, out=dwhh, split_ok=True)
+                        dwhh = gemm(pa, 768, False, pb, 512, False, 768, 256, rows, st, out=_empty((768, 256), dev),
+                                    split_ok=True, lazy={})
                     else:
                         dwhh = torch.zeros((768, 256), device=dev)
                     grads[id(getattr(gru, "weight_hh_" + nm))] = dwhh
-                    gemm(dgi[d], 768, True, w_ih, isz, False, TN, isz, 768, st, out=d_in, accumulate=(d == 1), b_weight=True)
+                    gemm(dgi[d], 768, True, wsplit.get(id(w_ih), w_ih), isz, False, TN, isz, 768, st, out=d_in, accumulate=(d == 1), b_weight=True)
                 d_out = d_in
             d_seq = d_out  # [T, N, 128]
 
@@ -381,8 +427,8 @@ class _RecFunction(torch.autograd.Function):
                 coef = _empty((5, cout), dev)
                 call("ocrs_bn_bwd_finalize", ptr(part), blocks, cout, float(N * Ho * Wo), ptr(bn.weight), ptr(bs.mean),
                      ptr(bs.invstd), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), int(training), st)
-                grads[id(bn.weight)] = coef[0].clone()
-                grads[id(bn.bias)] = coef[1].clone()
+                grads[id(bn.weight)] = coef[0]
+                grads[id(bn.bias)] = coef[1]
                 dy = _empty((N, Ho, Wo, cout), dev)
                 call("ocrs_rec_bn_act_pool_bwd_apply", ptr(y), N, Ho, Wo, cout, ph, pw, mode, relu, ptr(bs.scale),
                      ptr(bs.shift), ptr(coef[2]), ptr(coef[3]), ptr(coef[4]), ptr(dout), *dstr, ptr(dy), st)
@@ -399,17 +445,17 @@ class _RecFunction(torch.autograd.Function):
                     dwp = conv3x3_wgrad(dy, r["inp"], N, Hh, Ww, cin, cout, st)
                 else:
                     M, K = col.shape
-                    dwp = gemm(dy, cout, False, col, K, False, cout, K, M, st, split_ok=True)
-                grads[id(conv.weight)] = _w_grad_back(dwp, conv.weight)
+                    dwp = gemm(dy, cout, False, col, K, False, cout, K, M, st, split_ok=True, lazy=dict(conv=(cin, kh * kh)))
+                grads[id(conv.weight)] = dwp  # [Cout][(ky,kx,ci)] rows; grads.deliver writes the parameter layout
                 if conv.bias is not None:
                     grads[id(conv.bias)] = colsum(dy, cout, M, cout, st, dev)
                 if not need_dx:
                     return None
                 if _implicit_ok(cout, kh):
-                    return conv3x3(dy, N, Ho, Wo, cout, _w_dgrad(conv.weight), cin, st)
+                    return conv3x3(dy, N, Ho, Wo, cout, wdg[id(conv.weight)], cin, st)
                 dcol, Hi, Wi = im2col(dy, N, Ho, Wo, cout, kh, kh, kh - 1 - pad, kh - 1 - pad, st)
                 assert (Hi, Wi) == (Hh, Ww)
-                return gemm(dcol, dcol.shape[1], True, _w_dgrad(conv.weight), dcol.shape[1], True, N * Hh * Ww, cin,
+                return gemm(dcol, dcol.shape[1], True, wdg[id(conv.weight)], dcol.shape[1], True, N * Hh * Ww, cin,
                             dcol.shape[1], st, b_weight=True)
 
             r = rec["19"]
@@ -436,12 +482,11 @@ class _RecFunction(torch.autograd.Function):
             blocks = lib.ocrs_rec_conv0_bwd_blocks()
             part = _empty((blocks, 32, 10), dev)
             call("ocrs_rec_conv0_bwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(d_a0), ptr(part), st)
-            wb = _empty((32, 10), dev)
-            call("ocrs_finalize_partials", ptr(part), blocks, 320, ptr(wb), st)
-            grads[id(cv["0"].weight)] = wb[:, :9].reshape(32, 1, 3, 3).contiguous()
-            grads[id(cv["0"].bias)] = wb[:, 9].contiguous()
-        ctx.rec = ctx.gru_rec = ctx.misc = None
-        return (None, None) + tuple(grads.get(id(p)) for p in model.parameters())
+            grads[id(cv["0"].weight)] = Partial(part, blocks, 288, ld=320, inner=(9, 10))
+            grads[id(cv["0"].bias)] = Partial(part, blocks, 32, ld=320, off=9, inner=(1, 10))
+            param_grads = deliver(list(model.parameters()), grads, st)
+        ctx.rec = ctx.gru_rec = ctx.misc = ctx.wprep = None
+        return (None, None) + tuple(param_grads)
 
 
 _env_mode_applied = False

@@ -77,8 +77,11 @@ def test_separable_block_fwd_bwd(N, cin, cout, H, W, with_xf):
     torch.cuda.synchronize()
     assert rel_l2(dx.t, xa.grad) < 2e-4, "dx"
     names = ["b.seq.0.weight", "b.seq.1.weight", "b.seq.2.weight", "b.seq.2.bias"]
+    from ocrs_models_b200.grads import materialize
+
     for gname, got in zip(names, grads):
         want = sd[gname].grad
+        got = materialize(got, tuple(want.shape), _stream())  # weight gradients leave the block as partial rows
         err = (got.cpu().double() - want).norm() / max(want.norm(), 1e-3 * d_a.numel() ** 0.5)
         assert err < 1e-3, (gname, float(err))
 
@@ -308,7 +311,9 @@ def test_convt_as_tcgen05_gemms(N, cin, cout, h, w, Hs, Ws):
     dlo = E.View(dcat, 0, (cout + 3) * Hs * Ws, cout, Hs, Ws)
     d_up, dw = E._convt_backward_tc(t, xa, dlo, N, cin, h, w, _stream())
     assert rel_l2(d_up.t, a.grad) < 2e-6
-    assert rel_l2(dw, wt.grad) < 2e-6
+    from ocrs_models_b200.grads import materialize
+
+    assert rel_l2(materialize(dw, (cin, cout, 3, 3), _stream()), wt.grad) < 2e-6
 
 
 def _loss_case(p, t):

@@ -122,13 +122,15 @@ def test_implicit_gemm_conv3x3(N, H, W, cin, cout):
     dx = conv3x3(dyd, N, H, W, cout, _w_dgrad(w.cuda()), cin, _st())
     assert rel_l2(dx.reshape(N, H, W, cin).permute(0, 3, 1, 2), dref) < 3e-6
     # weight gradient, also gathered by TMA (no im2col buffer)
-    from ocrs_models_b200.rec_engine import _w_grad_back, conv3x3_wgrad
+    from ocrs_models_b200.grads import materialize
+    from ocrs_models_b200.rec_engine import conv3x3_wgrad
 
     xg = x.double().requires_grad_(True)
     wg = w.double().requires_grad_(True)
     F.conv2d(xg, wg, None, padding=1).backward(dy.double())
     dwp = conv3x3_wgrad(dyd.reshape(N * H * W, cout), xd, N, H, W, cin, cout, _st())
-    assert rel_l2(_w_grad_back(dwp, w), wg.grad) < 5e-6
+    # split-K partial rows in the GEMM layout [cout][(ky,kx,ci)]; the multi-tensor delivery kernel reduces and re-lays them out
+    assert rel_l2(materialize(dwp, w.shape, _st()), wg.grad) < 5e-6
 
 
 def test_conv0_fwd_bwd():
