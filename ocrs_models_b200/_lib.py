@@ -102,7 +102,7 @@ SIGNATURES: dict[str, list] = {
     "ocrs_gru_layer_fwd_persist": [P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_gru_layer_bwd_persist": [P, P, P, P, P, P, P, P, P, I, I, P],
     "ocrs_log_softmax_fwd": [P, P, I, I, P],
-    "ocrs_log_softmax_bwd": [P, P, P, I, I, P],
+    "ocrs_log_softmax_bwd": [P, P, P, I, I, I, P],
     "ocrs_transpose": [P, P, I, I, P],
     # recognition accuracy bookkeeping (csrc/metrics.cu)
     "ocrs_ctc_greedy_cer_max_targets": [],

@@ -30,13 +30,16 @@ struct GradTable {
   int count;
 };
 
-__device__ __forceinline__ int gd_col(int k, int map, int p0, int p1) {
-  if (map == 1) {  // dst [co][ci][t] <- src [co][t][ci]
-    const int t = k % p1, r = k / p1, ci = r % p0, co = r / p0;
-    return (co * p1 + t) * p0 + ci;
+// Work item k of an entry -> (source column, destination index). The convolution re-layout walks the SOURCE in order
+// (coalesced partial-row reads, one scattered store per element); the other maps walk the destination.
+__device__ __forceinline__ void gd_index(int k, int map, int p0, int p1, int& col, int& di) {
+  col = k; di = k;
+  if (map == 1) {  // src [co][t][ci] -> dst [co][ci][t]
+    const int ci = k % p0, r = k / p0, t = r % p1, co = r / p1;
+    di = (co * p0 + ci) * p1 + t;
+  } else if (map == 2) {
+    col = (k / p0) * p1 + (k % p0);
   }
-  if (map == 2) return (k / p0) * p1 + (k % p0);
-  return k;
 }
 
 // "wide" entries (few rows, many columns): 256 threads x 4 consecutive columns, rows summed by the thread.
@@ -56,7 +59,18 @@ __global__ void __launch_bounds__(256) grad_deliver_kernel(const __grid_constant
     if (k0 >= K) return;
     if (map == 0 && k0 + 4 <= K && ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) && (ld & 3) == 0) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      for (int r = 0; r < rows; ++r) {
+      int r = 0;
+      for (; r + 3 < rows; r += 4) {  // four rows in flight
+        const float4 a = *reinterpret_cast<const float4*>(src + (size_t)r * ld + k0);
+        const float4 c = *reinterpret_cast<const float4*>(src + (size_t)(r + 1) * ld + k0);
+        const float4 d = *reinterpret_cast<const float4*>(src + (size_t)(r + 2) * ld + k0);
+        const float4 f = *reinterpret_cast<const float4*>(src + (size_t)(r + 3) * ld + k0);
+        s0 += ((double)a.x + (double)c.x) + ((double)d.x + (double)f.x);
+        s1 += ((double)a.y + (double)c.y) + ((double)d.y + (double)f.y);
+        s2 += ((double)a.z + (double)c.z) + ((double)d.z + (double)f.z);
+        s3 += ((double)a.w + (double)c.w) + ((double)d.w + (double)f.w);
+      }
+      for (; r < rows; ++r) {
         const float4 a = *reinterpret_cast<const float4*>(src + (size_t)r * ld + k0);
         s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
       }
@@ -68,19 +82,24 @@ __global__ void __launch_bounds__(256) grad_deliver_kernel(const __grid_constant
       *reinterpret_cast<float4*>(dst + k0) = o;
       return;
     }
-    for (int q = 0; q < 4 && k0 + q < K; ++q) {
-      const int c = gd_col(k0 + q, map, p0, p1);
-      double s = 0.0;
-      for (int r = 0; r < rows; ++r) s += (double)src[(size_t)r * ld + c];
-      dst[k0 + q] = acc ? dst[k0 + q] + (float)s : (float)s;
-    }
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    int c[4], di[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gd_index(min(k0 + q, K - 1), map, p0, p1, c[q], di[q]);
+    for (int r = 0; r < rows; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += (double)src[(size_t)r * ld + c[q]];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (k0 + q < K) dst[di[q]] = acc ? dst[di[q]] + (float)s[q] : (float)s[q];
     return;
   }
   const int kx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int k = b * 32 + kx;
   double s = 0.0;
+  int c = 0, di = 0;
   if (k < K) {
-    const int c = gd_col(k, map, p0, p1);
+    gd_index(k, map, p0, p1, c, di);
     int r = ry;
     for (; r + 24 < rows; r += 32) {
       const float v0 = src[(size_t)r * ld + c], v1 = src[(size_t)(r + 8) * ld + c];
@@ -95,7 +114,7 @@ __global__ void __launch_bounds__(256) grad_deliver_kernel(const __grid_constant
     double t = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) t += red[q][kx];
-    dst[k] = acc ? dst[k] + (float)t : (float)t;
+    dst[di] = acc ? dst[di] + (float)t : (float)t;
   }
 }
 
@@ -170,7 +189,9 @@ int ocrs_grad_deliver(const float* const* src, float* const* dst, const int* K, 
   for (int e = 0; e < count; ++e) {
     OCRS_CHECK_ARG(src[e] && dst[e] && K[e] > 0 && rows[e] > 0 && map[e] >= 0 && map[e] <= 2, "grad_deliver: bad entry %d", e);
     OCRS_CHECK_ARG(map[e] == 0 || (p0[e] > 0 && p1[e] > 0), "grad_deliver: bad column map of entry %d", e);
-    const bool wide = rows[e] < 16;
+    // many columns: one thread per 4 columns walks the rows (split-K partials of the big GEMM gradients have up to ~100 rows);
+    // few columns and many rows (per-CTA partials): 8 row lanes per column
+    const bool wide = rows[e] < 16 || (K[e] >= 8192 && rows[e] <= 256);
     t.src[e] = src[e]; t.dst[e] = dst[e]; t.K[e] = K[e]; t.rows[e] = rows[e]; t.ld[e] = ld[e];
     t.flags[e] = map[e] | (accumulate[e] ? 4 : 0) | (wide ? 8 : 0);
     t.p0[e] = p0[e]; t.p1[e] = p1[e];

@@ -499,14 +499,14 @@ __global__ void log_softmax_fwd_kernel(const float* __restrict__ x, float* __res
   for (int c = lane; c < C; c += 32) y[(size_t)row * C + c] = xr[c] - lse;
 }
 __global__ void log_softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g,
-                                       float* __restrict__ dx, int R, int C) {
+                                       float* __restrict__ dx, int R, int C, int ld_dx) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   float s = 0.f;
   for (int c = lane; c < C; c += 32) s += g[(size_t)row * C + c];
   s = warp_sum(s);
-  for (int c = lane; c < C; c += 32)
-    dx[(size_t)row * C + c] = g[(size_t)row * C + c] - expf(y[(size_t)row * C + c]) * s;
+  for (int c = lane; c < ld_dx; c += 32)  // columns C .. ld_dx-1 are zero padding (16-byte row pitch for the TMA GEMMs)
+    dx[(size_t)row * ld_dx + c] = c < C ? g[(size_t)row * C + c] - expf(y[(size_t)row * C + c]) * s : 0.f;
 }
 
 // dst[c][r] = src[r][c] (small weight transposes)
@@ -619,8 +619,10 @@ int ocrs_log_softmax_fwd(const float* x, float* y, int R, int C, void* stream) {
   OCRS_CHECK_LAUNCH("log_softmax_fwd_kernel");
   return 0;
 }
-int ocrs_log_softmax_bwd(const float* y, const float* g, float* dx, int R, int C, void* stream) {
-  log_softmax_bwd_kernel<<<ocrs_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(y, g, dx, R, C);
+// dx [R][ld_dx] (ld_dx >= C; the padding columns are written as zeros) from y = log_softmax(x) [R][C] and g = dL/dy [R][C].
+int ocrs_log_softmax_bwd(const float* y, const float* g, float* dx, int R, int C, int ld_dx, void* stream) {
+  OCRS_CHECK_ARG(ld_dx >= C, "log_softmax_bwd: row pitch %d < %d columns", ld_dx, C);
+  log_softmax_bwd_kernel<<<ocrs_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(y, g, dx, R, C, ld_dx);
   OCRS_CHECK_LAUNCH("log_softmax_bwd_kernel");
   return 0;
 }

@@ -378,12 +378,13 @@ class _RecFunction(torch.autograd.Function):
         grads = {}
         g_lp = g_lp.contiguous().float()
         with torch.cuda.device(dev):
-            dlog = _empty((TN, C), dev)
-            call("ocrs_log_softmax_bwd", ptr(lp), ptr(g_lp), ptr(dlog), TN, C, st)
+            ldd = (C + 3) // 4 * 4  # 16-byte row pitch (C = 97 -> 100): the two GEMMs below can then take dlog by TMA
+            dlog = _empty((TN, ldd), dev)
+            call("ocrs_log_softmax_bwd", ptr(lp), ptr(g_lp), ptr(dlog), TN, C, ldd, st)
             out1 = gru_rec[1]["out"]
-            grads[id(lin.weight)] = gemm(dlog, C, False, out1, 512, False, C, 512, TN, st, split_ok=True, lazy={})
-            grads[id(lin.bias)] = colsum(dlog, C, TN, C, st, dev)
-            d_out = gemm(dlog, C, True, wsplit.get(id(lin.weight), lin.weight), 512, False, TN, 512, C, st, b_weight=True)
+            grads[id(lin.weight)] = gemm(dlog, ldd, False, out1, 512, False, C, 512, TN, st, split_ok=True, lazy={})
+            grads[id(lin.bias)] = colsum(dlog, ldd, TN, C, st, dev)
+            d_out = gemm(dlog, ldd, True, wsplit.get(id(lin.weight), lin.weight), 512, False, TN, 512, C, st, b_weight=True)
             for layer in (1, 0):
                 r = gru_rec[layer]
                 isz, xin, out, gates = r["isz"], r["x"], r["out"], r["gates"]

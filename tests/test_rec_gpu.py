@@ -215,8 +215,12 @@ def test_log_softmax():
     assert rel_l2(y, ref) < 1e-6
     dx = torch.empty_like(xd)
     gd = gr.cuda()
-    call("ocrs_log_softmax_bwd", ptr(y), ptr(gd), ptr(dx), 77, 97, _st())
+    call("ocrs_log_softmax_bwd", ptr(y), ptr(gd), ptr(dx), 77, 97, 97, _st())
     assert rel_l2(dx, x.grad) < 1e-5
+    # padded row pitch (what the engine uses so that the head's gradient GEMMs can take dlog by TMA): zeros in the padding
+    dxp = torch.full((77, 100), float("nan"), device="cuda")
+    call("ocrs_log_softmax_bwd", ptr(y), ptr(gd), ptr(dxp), 77, 97, 100, _st())
+    assert torch.equal(dxp[:, :97], dx) and dxp[:, 97:].abs().max().item() == 0
 
 
 def _rec_model(seed=1234):
