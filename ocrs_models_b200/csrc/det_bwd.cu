@@ -886,6 +886,9 @@ convt_im2col_kernel(const float* __restrict__ dout, long long dout_ss, int Cout,
 
 }  // namespace
 
+bool ocrs_convt_mma_bwd(const float* dout, long long dout_ss, int N, int Cout, int Hs, int Ws, const float* w, int Cin, int Hin,
+                        int Win, float* dx, long long dx_ss, cudaStream_t st);  // csrc/det_convt.cu
+
 extern "C" {
 
 int ocrs_finalize_partials(const float* partials, int nblk, int K, float* out, void* stream) {
@@ -1074,6 +1077,10 @@ int ocrs_det_convt_bwd_data(const float* dout, long long dout_ss, int N, int Cou
                             void* stream) {
   dim3 block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if (ocrs_convt_mma_bwd(dout, dout_ss, N, Cout, Hs, Ws, w, Cin, Hin, Win, dx, dx_ss, st)) {  // csrc/det_convt.cu
+    OCRS_CHECK_LAUNCH("convt_bwd_mma_kernel");
+    return 0;
+  }
   if (Cin <= 8) {
     dim3 grid(ocrs_cdiv(Win, 32), ocrs_cdiv(Hin, 8), N * ocrs_cdiv(Cin, 8));
     convt_bwd_data_kernel<8><<<grid, block, 0, st>>>(dout, dout_ss, Cout, Hs, Ws, w, Cin, Hin, Win, dx, dx_ss);

@@ -431,6 +431,10 @@ convt_col2im_kernel(const float* __restrict__ Z /*[N][Cout*9][Hin*Win]*/, int Co
 
 }  // namespace
 
+bool ocrs_convt_mma_fwd(const float* x, long long x_ss, int N, int Cin, int Hin, int Win, const float* sc, const float* sh,
+                        const float* lo, const float* w, const float* bias, int Cout, float* out, long long out_ss, int Hs,
+                        int Ws, cudaStream_t st);  // csrc/det_convt.cu
+
 extern "C" {
 
 // a[n][c][p] = max(x * scale + shift, lo) (the producer's folded BatchNorm + ReLU) written contiguously as [N][C][HW]:
@@ -535,6 +539,11 @@ int ocrs_det_convt_fwd(const float* x, long long x_ss, int N, int Cin, int Hin, 
   const int QH = (Hs + 1) / 2, QW = (Ws + 1) / 2;
   dim3 block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
+  // 16-32 channel levels on TMA-friendly shapes: tensor-core tile kernel (csrc/det_convt.cu)
+  if (ocrs_convt_mma_fwd(x, x_ss, N, Cin, Hin, Win, sc, sh, lo, w, bias, Cout, out, out_ss, Hs, Ws, st)) {
+    OCRS_CHECK_LAUNCH("convt_fwd_mma_kernel");
+    return 0;
+  }
   if (Cout <= 8) {
     dim3 grid(ocrs_cdiv(QW, 32), ocrs_cdiv(QH, 8), N * ocrs_cdiv(Cout, 8));
     convt_fwd_kernel<8><<<grid, block, 0, st>>>(x, x_ss, Cin, Hin, Win, sc, sh, lo, w, bias, Cout,
