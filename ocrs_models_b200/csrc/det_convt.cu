@@ -47,7 +47,7 @@ constexpr int FPL = ((FQH + 1) * FXC / 32) * 32 + 8;     // plane stride = 8 mod
 static_assert(FPL >= (FQH + 1) * FXC, "plane stride");
 
 template <int CI, int CO>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (CI == 32 && CO == 32) ? 1 : 2)
 convt_fwd_mma_kernel(ConvtArgs a) {
   constexpr int WS = wstride(CO), NT = CO / 8, KS = CI / 8;
   extern __shared__ __align__(16) float smem[];
@@ -67,28 +67,48 @@ convt_fwd_mma_kernel(ConvtArgs a) {
   for (int nt = 0; nt < NT; ++nt) { bias[nt][0] = a.bias ? a.bias[8 * nt + 2 * t] : 0.f; bias[nt][1] = a.bias ? a.bias[8 * nt + 2 * t + 1] : 0.f; }
   const long long tiles = (long long)a.N * a.tiles_y * a.tiles_x;
   const size_t HWi = (size_t)a.Hin * a.Win, HWs = (size_t)a.Hs * a.Ws;
+  // The tile is staged through registers one tile ahead (three CTAs per SM with 80 registers were slower than two with 124): the global loads of tile i+1 are in flight while tile i is
+  // contracted (the kernel has too few resident warps to hide that latency otherwise: ncu long-scoreboard stalls).
+  constexpr int TOTAL = CI * (FQH + 1) * (FXC / 4), NLD = (TOTAL + 255) / 256;
+  float4 pre[NLD];
+  unsigned inside = 0;  // bit u: pre[u] is inside the image (gets the BatchNorm+ReLU transform; outside stays 0)
+  auto fetch = [&](long long tile) {
+    const int tx = (int)(tile % a.tiles_x), ty = (int)((tile / a.tiles_x) % a.tiles_y), n = (int)(tile / ((long long)a.tiles_x * a.tiles_y));
+    const float* xn = a.x + (size_t)n * a.x_ss;
+    inside = 0;
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + 256 * u;
+      const int c4 = i % (FXC / 4), r = (i / (FXC / 4)) % (FQH + 1), ci = i / ((FXC / 4) * (FQH + 1));
+      const int iy = ty * FQH - 1 + r, ix = tx * FQW - 4 + 4 * c4;
+      pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < TOTAL && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {  // Win % 4 == 0: the four columns are in or out together
+        pre[u] = *reinterpret_cast<const float4*>(xn + (size_t)ci * HWi + (size_t)iy * a.Win + ix);
+        inside |= 1u << u;
+      }
+    }
+  };
+  if ((long long)blockIdx.x < tiles) fetch(blockIdx.x);
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int tx = (int)(tile % a.tiles_x), ty = (int)((tile / a.tiles_x) % a.tiles_y), n = (int)(tile / ((long long)a.tiles_x * a.tiles_y));
     const int qy0 = ty * FQH, qx0 = tx * FQW;
     __syncthreads();  // the previous tile's fragments have been read (and the weights are in place)
-    // stage rows qy0-1 .. qy0+FQH-1, columns qx0-4 .. qx0+31 of every channel, BatchNorm+ReLU applied, 0 outside the image
-    const float* xn = a.x + (size_t)n * a.x_ss;
+    // rows qy0-1 .. qy0+FQH-1, columns qx0-4 .. qx0+31 of every channel, BatchNorm+ReLU applied, 0 outside the image
 #pragma unroll
-    for (int i = tid; i < CI * (FQH + 1) * (FXC / 4); i += 256) {
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + 256 * u;
+      if (i >= TOTAL) break;
       const int c4 = i % (FXC / 4), r = (i / (FXC / 4)) % (FQH + 1), ci = i / ((FXC / 4) * (FQH + 1));
-      const int iy = qy0 - 1 + r, ix = qx0 - 4 + 4 * c4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) {  // Win % 4 == 0: the four columns are in or out together
-        v = *reinterpret_cast<const float4*>(xn + (size_t)ci * HWi + (size_t)iy * a.Win + ix);
-        if (a.sc) {
-          const float s = a.sc[ci], h = a.sh[ci], l = a.lo[ci];
-          v.x = xform_apply(v.x, s, h, l); v.y = xform_apply(v.y, s, h, l);
-          v.z = xform_apply(v.z, s, h, l); v.w = xform_apply(v.w, s, h, l);
-        }
+      float4 v = pre[u];
+      if (a.sc && ((inside >> u) & 1u)) {
+        const float s = a.sc[ci], h = a.sh[ci], l = a.lo[ci];
+        v.x = xform_apply(v.x, s, h, l); v.y = xform_apply(v.y, s, h, l);
+        v.z = xform_apply(v.z, s, h, l); v.w = xform_apply(v.w, s, h, l);
       }
       *reinterpret_cast<float4*>(xs + ci * FPL + r * FXC + 4 * c4) = v;
     }
     __syncthreads();
+    if (tile + gridDim.x < tiles) fetch(tile + gridDim.x);
     const int qy = qy0 + warp;
     if (qy >= a.QH) continue;  // (whole warp; the barriers above are reached through the loop head)
 #pragma unroll 1
@@ -155,7 +175,7 @@ constexpr int BPL = ((BROWS * 2 * BDC) / 32) * 32 + 8;   // 648 for BQH = 4 (= 8
 static_assert(BPL >= BROWS * 2 * BDC, "plane stride");
 
 template <int CI, int CO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CO == 32 ? 1 : 2)
 convt_bwd_mma_kernel(ConvtArgs a) {
   constexpr int WS = wstride(CI), NT = CI / 8, KS = CO / 8;
   extern __shared__ __align__(16) float smem[];
@@ -173,23 +193,38 @@ convt_bwd_mma_kernel(ConvtArgs a) {
   const long long tiles = (long long)a.N * a.tiles_y * a.tiles_x;
   const size_t HWi = (size_t)a.Hin * a.Win, HWs = (size_t)a.Hs * a.Ws;
   float* dx = const_cast<float*>(a.x);
+  constexpr int TOTAL = CO * BROWS * 18, NLD = (TOTAL + 255) / 256;
+  float4 pre[NLD];  // the next tile, in flight while this one is contracted
+  auto fetch = [&](long long tile) {
+    const int tx = (int)(tile % a.tiles_x), ty = (int)((tile / a.tiles_x) % a.tiles_y), n = (int)(tile / ((long long)a.tiles_x * a.tiles_y));
+    const float* dn = a.out + (size_t)n * a.out_ss;
+    // rows 2 qy0 .. 2 qy0 + 2 BQH, columns 2 qx0 .. 2 qx0 + 71 (18 float4; Ws % 4 == 0), 0 outside the crop
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + 256 * u;
+      const int c4 = i % 18, r = (i / 18) % BROWS, co = i / (18 * BROWS);
+      const int oy = 2 * ty * BQH + r, ox = 2 * tx * BQW + 4 * c4;
+      pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < TOTAL && oy < a.Hs && ox < a.Ws) pre[u] = *reinterpret_cast<const float4*>(dn + (size_t)co * HWs + (size_t)oy * a.Ws + ox);
+    }
+  };
+  if ((long long)blockIdx.x < tiles) fetch(blockIdx.x);
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int tx = (int)(tile % a.tiles_x), ty = (int)((tile / a.tiles_x) % a.tiles_y), n = (int)(tile / ((long long)a.tiles_x * a.tiles_y));
     const int qy0 = ty * BQH, qx0 = tx * BQW;
     __syncthreads();
-    const float* dn = a.out + (size_t)n * a.out_ss;
-    // rows 2 qy0 .. 2 qy0 + 2 BQH, columns 2 qx0 .. 2 qx0 + 71 (18 float4; Ws % 4 == 0), 0 outside the crop
 #pragma unroll
-    for (int i = tid; i < CO * BROWS * 18; i += 256) {
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + 256 * u;
+      if (i >= TOTAL) break;
       const int c4 = i % 18, r = (i / 18) % BROWS, co = i / (18 * BROWS);
-      const int oy = 2 * qy0 + r, ox = 2 * qx0 + 4 * c4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (oy < a.Hs && ox < a.Ws) v = *reinterpret_cast<const float4*>(dn + (size_t)co * HWs + (size_t)oy * a.Ws + ox);
+      const float4 v = pre[u];
       float* row = ds + co * BPL + r * 2 * BDC;
       *reinterpret_cast<float2*>(row + 2 * c4) = make_float2(v.x, v.z);        // even columns ox, ox + 2
       *reinterpret_cast<float2*>(row + BDC + 2 * c4) = make_float2(v.y, v.w);  // odd columns
     }
     __syncthreads();
+    if (tile + gridDim.x < tiles) fetch(tile + gridDim.x);
     const int qy = qy0 + (warp >> 1), qxb = qx0 + 16 * (warp & 1);
     if (qy >= a.Hin || qxb >= a.Win) continue;
     float acc[NT][4];
