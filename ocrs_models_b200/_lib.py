@@ -81,6 +81,8 @@ SIGNATURES: dict[str, list] = {
     "ocrs_gemm_tc": [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_gemm_tc_splits": [I, I],
     "ocrs_gemm_tc_batched": [P, L, I, I, I, P, L, I, I, I, P, L, L, I, I, I, I, P, P],
+    "ocrs_gemm_tc_batched_splits": [I, I],
+    "ocrs_gemm_tc_batched_splitk": [P, L, I, I, I, P, L, I, I, I, P, L, L, I, I, I, I, I, P],
     "ocrs_gemm_tc_batched_stat_rows": [I, I],
     "ocrs_gemm_tc_presplit": [P, L, I, P, P, L, I, P, L, I, I, I, P, I, I, P, I, P],
     "ocrs_conv3x3_tc_presplit": [P, I, I, I, I, P, P, I, P, L, P, I, P, P],

@@ -58,8 +58,9 @@ struct TcArgs {
   int b_split;               // B arrives pre-split (map_b = TF32-exact hi, map_b2 = lo): weights, split once per step
   // Batched GEMM (detection deep levels): tile index z = batch item. Operands are 2-D matrices in which the items are
   // stacked along the ROW axis of the tensor map (planar [N][C][HW] tensors: row = n*C + c), so an item is a row offset;
-  // every item runs the full K range; C advances by c_zstride elements per item.
-  int batched, a_brows, b_brows;
+  // every item runs the full K range, or bsplit slices of it (z = item * bsplit + slice: weight gradients, whose K is
+  // the pixel axis); C advances by c_zstride elements per z.
+  int batched, a_brows, b_brows, bsplit;
   long long c_zstride;       // elements between consecutive z slices of C (split-K partials: M * ldc)
   float* row_stats;          // [zs * tiles_n][2][M] per-row sum / sum of squares of the tile's columns (BatchNorm over N), or null
   int fast;                  // labelled throughput mode: ONE plain TF32 product per k-step (the tensor core truncates the
@@ -193,11 +194,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 #define TILE_DECODE(tile_)                                         \
   const int tn_ = (tile_) % g.tiles_n, tr_ = (tile_) / g.tiles_n;  \
-  const int tm_ = tr_ % g.tiles_m, tz_ = tr_ / g.tiles_m;          \
+  const int tm_ = tr_ % g.tiles_m, tzz_ = tr_ / g.tiles_m;         \
+  /* batched: z = (item, K split); tz_ = item (row offsets), tzz_ = output slice */ \
+  const int tz_ = g.batched ? tzz_ / g.bsplit : tzz_;              \
   const int m0 = tm_ * TBM, n0 = tn_ * g.bn;                       \
-  const int kb0 = g.batched ? 0 : tz_ * g.kb_per_split;            \
+  const int kb0 = (g.batched ? tzz_ % g.bsplit : tzz_) * g.kb_per_split; \
   const int nkb = min(total_kb, kb0 + g.kb_per_split) - kb0;       \
-  (void)m0; (void)n0; (void)kb0; (void)tz_; (void)tm_;
+  (void)m0; (void)n0; (void)kb0; (void)tz_; (void)tm_; (void)tzz_;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -405,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = m0 + q * 32 + lane;   // output row held by this thread
       const bool row_ok = m < g.M;
-      float* crow = g.C + (size_t)tz_ * g.c_zstride + (size_t)(row_ok ? m : 0) * g.ldc;
+      float* crow = g.C + (size_t)tzz_ * g.c_zstride + (size_t)(row_ok ? m : 0) * g.ldc;
       float rs1 = 0.f, rs2 = 0.f;  // row statistics of this tile (g.row_stats)
       const int n_main = min(3, nkb);
       const uint32_t lane_addr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
@@ -648,16 +651,12 @@ int ocrs_gemm_tc_presplit(const float* A, long long lda, int a_kmajor, const flo
   return gemm_tc_impl(A, lda, a_kmajor, B_hi, B_lo, ldb, b_kmajor, C, ldc, M, N, K, bias, relu, accumulate, stats, splits, stream);
 }
 
-// Batched C[z] = op(A[z]) op(B[z]) on the same tcgen05 kernel, z < batch, for operands whose items are stacked along
-// the row axis of a 2-D matrix (planar NCHW activations: row = n*C + c, row pitch H*W). a_brows / b_brows = rows per
-// item (0: the operand is shared by all items, e.g. a weight matrix); a_rows / b_rows = total rows of the 2-D matrix.
-// a_kmajor: A rows are M (each row K long), else rows are K (each row M long); same for B with N. C[z] starts at
-// C + z * c_batch_stride, row pitch ldc. row_stats (optional): [batch * ceil(N / bn)][2][M] per-row sums and sums of
-// squares (BatchNorm statistics over N when the rows are channels). Used by the detection levels with >= 64 channels.
-int ocrs_gemm_tc_batched(const float* A, long long lda, int a_kmajor, int a_rows, int a_brows, const float* B,
-                         long long ldb, int b_kmajor, int b_rows, int b_brows, float* C, long long ldc,
-                         long long c_batch_stride, int M, int N, int K, int batch, float* row_stats, void* stream) {
-  OCRS_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tc_batched: bad dims");
+static int gemm_tc_batched_impl(const float* A, long long lda, int a_kmajor, int a_rows, int a_brows, const float* B,
+                                long long ldb, int b_kmajor, int b_rows, int b_brows, float* C, long long ldc,
+                                long long c_batch_stride, int M, int N, int K, int batch, float* row_stats, int k_splits,
+                                void* stream) {
+  OCRS_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0 && k_splits >= 1, "gemm_tc_batched: bad dims");
+  OCRS_CHECK_ARG(k_splits == 1 || row_stats == nullptr, "gemm_tc_batched: row statistics need the whole K range per item");
   OCRS_CHECK_ARG(ocrs_gemm_tc_supported(A, lda, B, ldb), "gemm_tc_batched: operands must be 16-byte aligned with ld %% 4 == 0");
   OCRS_CHECK_ARG(K % TBK == 0 || (a_brows == 0 && b_brows == 0) || (a_kmajor && b_kmajor),
                  "gemm_tc_batched: K must be a multiple of 32 when items are stacked along K rows");
@@ -668,7 +667,8 @@ int ocrs_gemm_tc_batched(const float* A, long long lda, int a_kmajor, int a_rows
   if (b_kmajor) { if (make_map(&mb, B, K, b_rows, ldb, TBK, bn, false)) return -1; }
   else          { if (make_map(&mb, B, N, b_rows, ldb, 32, TBK, true)) return -1; }
   TcArgs g{C, ldc, M, N, K, nullptr, 0, 0, nullptr, 0, !a_kmajor, !b_kmajor, bn, 0, 0, 0, 0, 0};
-  g.kb_per_split = ocrs_cdiv(K, TBK);
+  g.kb_per_split = ocrs_cdiv(ocrs_cdiv(K, TBK), k_splits);
+  g.bsplit = ocrs_cdiv(ocrs_cdiv(K, TBK), g.kb_per_split);
   g.batched = 1;
   g.a_brows = a_brows;
   g.b_brows = b_brows;
@@ -676,7 +676,37 @@ int ocrs_gemm_tc_batched(const float* A, long long lda, int a_kmajor, int a_rows
   g.row_stats = row_stats;
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
             ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-  return launch_tc<0>(ma, mb, nullptr, g, ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), batch, (cudaStream_t)stream, "gemm_tc_kernel(batched)");
+  return launch_tc<0>(ma, mb, nullptr, g, ocrs_cdiv(N, bn), ocrs_cdiv(M, TBM), batch * g.bsplit, (cudaStream_t)stream, "gemm_tc_kernel(batched)");
+}
+
+// Batched C[z] = op(A[z]) op(B[z]) on the same tcgen05 kernel, z < batch, for operands whose items are stacked along
+// the row axis of a 2-D matrix (planar NCHW activations: row = n*C + c, row pitch H*W). a_brows / b_brows = rows per
+// item (0: the operand is shared by all items, e.g. a weight matrix); a_rows / b_rows = total rows of the 2-D matrix.
+// a_kmajor: A rows are M (each row K long), else rows are K (each row M long); same for B with N. C[z] starts at
+// C + z * c_batch_stride, row pitch ldc. row_stats (optional): [batch * ceil(N / bn)][2][M] per-row sums and sums of
+// squares (BatchNorm statistics over N when the rows are channels). Used by the detection levels with >= 64 channels.
+int ocrs_gemm_tc_batched(const float* A, long long lda, int a_kmajor, int a_rows, int a_brows, const float* B,
+                         long long ldb, int b_kmajor, int b_rows, int b_brows, float* C, long long ldc,
+                         long long c_batch_stride, int M, int N, int K, int batch, float* row_stats, void* stream) {
+  return gemm_tc_batched_impl(A, lda, a_kmajor, a_rows, a_brows, B, ldb, b_kmajor, b_rows, b_brows, C, ldc, c_batch_stride, M, N,
+                              K, batch, row_stats, 1, stream);
+}
+
+// K slices ocrs_gemm_tc_batched_splitk really uses when asked for `want` (whole 32-wide k-blocks per slice).
+int ocrs_gemm_tc_batched_splits(int K, int want) {
+  const int kb = ocrs_cdiv(K, TBK), per = ocrs_cdiv(kb, want < 1 ? 1 : want);
+  return ocrs_cdiv(kb, per);
+}
+
+// ocrs_gemm_tc_batched with every item's K range cut into ocrs_gemm_tc_batched_splits(K, k_splits) slices that run as
+// separate tiles: C holds batch * splits partial results, slice (item z, split s) at C + (z * splits + s) * c_batch_stride.
+// For the weight gradients of the detection levels, where K is the pixel axis of one sample and M x N is one tile.
+int ocrs_gemm_tc_batched_splitk(const float* A, long long lda, int a_kmajor, int a_rows, int a_brows, const float* B,
+                                long long ldb, int b_kmajor, int b_rows, int b_brows, float* C, long long ldc,
+                                long long c_batch_stride, int M, int N, int K, int batch, int k_splits, void* stream) {
+  OCRS_CHECK_ARG(a_kmajor && b_kmajor, "gemm_tc_batched_splitk: both operands must be K-major");
+  return gemm_tc_batched_impl(A, lda, a_kmajor, a_rows, a_brows, B, ldb, b_kmajor, b_rows, b_brows, C, ldc, c_batch_stride, M, N,
+                              K, batch, nullptr, k_splits, stream);
 }
 
 // Rows of the row_stats partials of ocrs_gemm_tc_batched.

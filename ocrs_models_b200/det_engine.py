@@ -162,10 +162,11 @@ class _Sep:
         g = new_view(N, ci, H, W, dev)
         call("ocrs_gemm_tc_batched", ptr(self.pw.weight), ci, 0, co, 0, ptr(dy), HW, 0, N * co, co, g.p, HW, g.ss,
              ci, HW, co, N, None, st, meta=2.0 * N * HW * ci * co)
-        wpart = torch.empty((N, co, ci), dtype=torch.float32, device=dev)
-        call("ocrs_gemm_tc_batched", ptr(dy), HW, 1, N * co, co, ptr(dwo), HW, 1, N * ci, ci, ptr(wpart), ci, co * ci,
-             co, ci, HW, N, None, st, meta=2.0 * N * HW * ci * co)
-        return g, Partial(wpart, N, co * ci)
+        ks = _wgrad_k_splits(HW, N, co, ci)
+        wpart = torch.empty((N * ks, co, ci), dtype=torch.float32, device=dev)
+        call("ocrs_gemm_tc_batched_splitk", ptr(dy), HW, 1, N * co, co, ptr(dwo), HW, 1, N * ci, ci, ptr(wpart), ci, co * ci,
+             co, ci, HW, N, ks, st, meta=2.0 * N * HW * ci * co)
+        return g, Partial(wpart, N * ks, co * ci)
 
     def backward(self, saved: dict, d_a: View, N, st, dx: View | None, accumulate=False, bn_pending=None):
         """d_a: gradient w.r.t. this block's activated output. Writes the gradient w.r.t. the
@@ -275,6 +276,15 @@ class _Plan:
         return ps
 
 
+def _wgrad_k_splits(HW, batch, M, Nn):
+    """K slices per sample for a batched weight-gradient GEMM (K = pixels of one sample): enough tiles to fill the GPU
+    twice, at least 512 pixels per slice."""
+    bn = 32 if Nn <= 32 else 64 if Nn <= 64 else 128
+    tiles = batch * ((M + 127) // 128) * ((Nn + bn - 1) // bn)
+    want = max(1, min(296 // max(tiles, 1), HW // 512))
+    return _lib.lib().ocrs_gemm_tc_batched_splits(HW, want)
+
+
 def _convt_tc_ok(t, up: View, cout):
     """ConvTranspose2d (models.py:76-78) as batched tcgen05 GEMMs: Z[n] = W^T x[n] with W read as [Cin][9*Cout]."""
     HW = up.H * up.W
@@ -305,10 +315,11 @@ def _convt_backward_tc(t, xa, dlo: View, N, ci, Hin, Win, st):
     d_up = new_view(N, ci, Hin, Win, dev)
     call("ocrs_gemm_tc_batched", ptr(t.weight), 9 * c, 1, ci, 0, ptr(dcol), HW, 0, N * 9 * c, 9 * c, d_up.p, HW, d_up.ss,
          ci, HW, 9 * c, N, None, st, meta=2.0 * N * HW * ci * 9 * c)
-    wpart = torch.empty((N, ci, 9 * c), dtype=torch.float32, device=dev)
-    call("ocrs_gemm_tc_batched", ptr(xa), HW, 1, N * ci, ci, ptr(dcol), HW, 1, N * 9 * c, 9 * c, ptr(wpart), 9 * c,
-         ci * 9 * c, ci, 9 * c, HW, N, None, st, meta=2.0 * N * HW * ci * 9 * c)
-    return d_up, Partial(wpart, N, ci * 9 * c)
+    ks = _wgrad_k_splits(HW, N, ci, 9 * c)
+    wpart = torch.empty((N * ks, ci, 9 * c), dtype=torch.float32, device=dev)
+    call("ocrs_gemm_tc_batched_splitk", ptr(xa), HW, 1, N * ci, ci, ptr(dcol), HW, 1, N * 9 * c, 9 * c, ptr(wpart), 9 * c,
+         ci * 9 * c, ci, 9 * c, HW, N, ks, st, meta=2.0 * N * HW * ci * 9 * c)
+    return d_up, Partial(wpart, N * ks, ci * 9 * c)
 
 
 _IDENT: dict = {}

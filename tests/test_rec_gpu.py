@@ -360,3 +360,13 @@ def test_batched_gemm_on_planar_activations(case, N, cin, cout, HW):
              cout, cin, HW, N, None, st)
         # the tensor core's truncating accumulation costs ~8e-7 per 1024 accumulated products
         assert rel_l2(part.double().sum(0), torch.einsum("nop,nip->oi", dy.double(), x.double())) < 1e-6 * max(3, HW / 1024 * 1.5)
+        # the same with every sample's pixel range cut into K slices (more tiles for the deep levels' small M x N)
+        ks = lib.ocrs_gemm_tc_batched_splits(HW, 3)
+        assert ks == (3 if HW >= 96 else 1)
+        part2 = torch.full((N * ks, cout, cin), float("nan"), device="cuda")
+        call("ocrs_gemm_tc_batched_splitk", ptr(dyd), HW, 1, N * cout, cout, ptr(xd), HW, 1, N * cin, cin, ptr(part2), cin,
+             cout * cin, cout, cin, HW, N, 3, st)
+        tol = 1e-6 * max(3, HW / 1024 * 1.5)
+        assert rel_l2(part2.double().sum(0), torch.einsum("nop,nip->oi", dy.double(), x.double())) < tol
+        per_sample = part2.view(N, ks, cout, cin).double().sum(1)
+        assert rel_l2(per_sample, torch.einsum("nop,nip->noi", dy.double(), x.double())) < tol
