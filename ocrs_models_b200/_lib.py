@@ -64,6 +64,8 @@ SIGNATURES: dict[str, list] = {
     "ocrs_det_sep_fwd": [P, L, I, I, I, I, P, P, P, P, P, I, P, L, P, P, P],
     "ocrs_det_pw_wgrad_saved_workers": [I, L, I, I],
     "ocrs_det_pw_wgrad_saved": [P, L, P, L, I, I, L, P, P, P, P, P, P, P, I, P, P, P, L, P],
+    "ocrs_det_pw_wgrad_saved32_workers": [I, L, I],
+    "ocrs_det_pw_wgrad_saved32": [P, L, P, L, I, L, P, P, P, P, P, P, P, I, P, P, P, L, P],
     "ocrs_det_sep_dw_bwd_rows": [I, I, I, I],
     "ocrs_det_sep_dw_bwd": [P, L, P, L, I, I, I, I, P, P, P, P, P, L, I, P, P, P, P, P],
     "ocrs_det_sep_pw_wgrad_workers": [I, I, I, I, I],

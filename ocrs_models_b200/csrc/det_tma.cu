@@ -928,6 +928,165 @@ pw_wgrad_saved_kernel(PwWg2Args a) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same for the blocks with 32 output channels (16->32, 32->32, 64->32: 8 of the 26 blocks). One CTA holds ALL 32
+// output channels of a 64-pixel stage (d_a 32 | y 32 | dwo 16 planes) and one 16-channel slice of the input channels,
+// so the 1x1 data gradient of its slice, g[ci][p] = sum_co Wpw[co][ci] * dy[co][p], is complete inside the CTA and
+// ocrs_det_pwT_bwd's separate pass over d_a and y (3.8 ms per detection step) disappears. The CTAs of the other input
+// slices re-read the same d_a / y chunk at the same time (L2 hits).
+constexpr int G32_PX = 64, G32_PS = G32_PX + 4, G32_PLANES = 80, G32_STAGE = G32_PLANES * G32_PS;
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+pw_wgrad_saved32_kernel(PwWg2Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);  // [GSTAGES][80][G32_PS]; reused for the final reduction
+  float* gs = stages + GSTAGES * G32_STAGE;            // [16][G32_PS] staging of the data gradient
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int ci0 = blockIdx.y * 16;
+  // A fragments of the g-mma (M = ci, K = co in four k-steps, slot permutation k = t -> co 2t, k = t + 4 -> co 2t + 1)
+  uint32_t wh[4][4], wl[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ci = g + 8 * (q & 1), co = 8 * ks + 2 * t + (q >> 1);
+      tf32_split2(a.wpw[(size_t)co * a.Cin + ci0 + ci], wh[ks][q], wl[ks][q]);
+    }
+  float ksc[4], ksh[4], klo[4], kk1[4], kk2[4], kk3[4];  // rows g + 8 h of the 32 output channels
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int o = g + 8 * h;
+    ksc[h] = a.sc[o]; ksh[h] = a.sh[o]; klo[h] = a.lo[o]; kk1[h] = a.k1[o]; kk2[h] = a.k2[o]; kk3[h] = a.k3[o];
+  }
+  float ctot[2][2][4], c[2][2][4];  // [co tile][ci tile]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ctot[m][j][q] = 0.f; c[m][j][q] = 0.f; }
+  const long long chunks_per_n = (a.HW + G32_PX - 1) / G32_PX;
+  const long long total = chunks_per_n * a.N;
+  const long long mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // cp.async requests of a stage: 80 planes x 16 columns of 16 bytes = 1280 = 5 per thread; request id = tid + 256 r
+  const float* pbase[5];
+  int pwhich[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int pl = (tid + 256 * r) >> 4;
+    pwhich[r] = pl < 32 ? 0 : (pl < 64 ? 1 : 2);
+    pbase[r] = pl < 32 ? a.d_a + (size_t)pl * a.HW : pl < 64 ? a.y + (size_t)(pl - 32) * a.HW : a.dwo + (size_t)(ci0 + pl - 64) * a.HW;
+  }
+  const long long dwo_ss = (long long)a.Cin * a.HW;
+  auto issue = [&](long long j) {
+    const long long w = blockIdx.x + j * gridDim.x;
+    const int n = (int)(w / chunks_per_n);
+    const long long p0 = (w - (long long)n * chunks_per_n) * G32_PX + 4 * (tid & 15);
+    const long long pc = p0 < a.HW ? p0 : 0;  // keep the (unread) source address inside the tensor
+    const long long off[3] = {(long long)n * a.da_ss + pc, (long long)n * a.y_ss + pc, (long long)n * dwo_ss + pc};
+    const long long rem = a.HW - p0;
+    const int bytes = rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0);  // < 16 zero-fills
+    const uint32_t dst = tma::smem_u32(stages + (j % GSTAGES) * G32_STAGE + (tid >> 4) * G32_PS + 4 * (tid & 15));
+#pragma unroll
+    for (int r = 0; r < 5; ++r) cp_async16(dst + r * 16 * G32_PS * 4, pbase[r] + off[pwhich[r]], bytes);
+  };
+  for (int j = 0; j < GSTAGES - 1; ++j) {
+    if (j < mine) issue(j);
+    cp_async_commit();
+  }
+  for (long long j = 0; j < mine; ++j) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();  // stage j landed for every thread; stage (j - 1) and gs are free again
+    if (j + GSTAGES - 1 < mine) issue(j + GSTAGES - 1);
+    cp_async_commit();
+    float* st = stages + (j % GSTAGES) * G32_STAGE;
+    const int px = warp * 8 + t;  // warp w owns pixels 8w .. 8w+7 of the stage (one k-step of the weight gradient)
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // q: 0 = (g, t), 1 = (g+8, t), 2 = (g, t+4), 3 = (g+8, t+4)
+        const int h = 2 * m + (q & 1), e = q >> 1, o = g + 8 * h;
+        const float da = st[o * G32_PS + px + 4 * e];
+        const float yv = st[(32 + o) * G32_PS + px + 4 * e];
+        const float dz = (fmaf(yv, ksc[h], ksh[h]) > klo[h]) ? da : 0.f;
+        const float dy = fmaf(kk1[h], dz, fmaf(kk2[h], yv, kk3[h]));  // pixels past HW: dy = k3, but dwo is zero-filled and g is not stored
+        tf32_split2(dy, ah[m][q], al[m][q]);
+        st[o * G32_PS + px + 4 * e] = dy;  // in place over d_a: only this warp reads these pixels
+      }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      uint32_t bh0, bl0, bh1, bl1;
+      tf32_split2(st[(64 + 8 * jj + g) * G32_PS + px], bh0, bl0);      // (k = t,     n = ci 8jj + g)
+      tf32_split2(st[(64 + 8 * jj + g) * G32_PS + px + 4], bh1, bl1);  // (k = t + 4, n = ci 8jj + g)
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma_tf32_16n8k8(c[m][jj], al[m], bh0, bh1);
+        mma_tf32_16n8k8(c[m][jj], ah[m], bl0, bl1);
+        mma_tf32_16n8k8(c[m][jj], ah[m], bh0, bh1);
+      }
+    }
+    // data gradient of this warp's 8 pixels: M = 16 input channels, N = 8 pixels, K = 32 output channels
+    __syncwarp();
+    {
+      float cg[4] = {0.f, 0.f, 0.f, 0.f}, cx[4] = {0.f, 0.f, 0.f, 0.f};  // hi.hi and cross terms apart
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t bh[2], bl[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)  // B: (k = t -> co 8ks + 2t, k = t+4 -> co 8ks + 2t + 1; n = pixel g)
+          tf32_split2(st[(8 * ks + 2 * t + e) * G32_PS + warp * 8 + g], bh[e], bl[e]);
+        mma_tf32_16n8k8(cx, wl[ks], bh[0], bh[1]);
+        mma_tf32_16n8k8(cx, wh[ks], bl[0], bl[1]);
+        mma_tf32_16n8k8(cg, wh[ks], bh[0], bh[1]);
+      }
+      // C fragment: c0 (ci g, px 2t), c1 (ci g, px 2t+1), c2 (ci g+8, px 2t), c3 (ci g+8, px 2t+1)
+      *reinterpret_cast<float2*>(gs + g * G32_PS + warp * 8 + 2 * t) = make_float2(cg[0] + cx[0], cg[1] + cx[1]);
+      *reinterpret_cast<float2*>(gs + (g + 8) * G32_PS + warp * 8 + 2 * t) = make_float2(cg[2] + cx[2], cg[3] + cx[3]);
+    }
+    __syncthreads();  // gs complete
+    {
+      const long long w = blockIdx.x + j * gridDim.x;
+      const int n = (int)(w / chunks_per_n);
+      const long long p0 = (w - (long long)n * chunks_per_n) * G32_PX + 4 * (tid & 15);
+      const int ci = tid >> 4;
+      if (p0 < a.HW)  // HW % 4 == 0: the four pixels are in or out together
+        *reinterpret_cast<float4*>(a.g + (size_t)n * a.g_ss + (size_t)(ci0 + ci) * a.HW + p0) =
+            *reinterpret_cast<const float4*>(gs + ci * G32_PS + 4 * (tid & 15));
+    }
+    if ((j & 7) == 7) {  // keep the tensor core's truncating accumulation chains short (8 k-steps)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { ctot[m][jj][q] += c[m][jj][q]; c[m][jj][q] = 0.f; }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float* sred = stages;  // [8][32 * 16]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      float* r0 = sred + warp * 512 + (16 * m + g) * 16 + 8 * jj + 2 * t;
+      r0[0] = ctot[m][jj][0] + c[m][jj][0];
+      r0[1] = ctot[m][jj][1] + c[m][jj][1];
+      r0[8 * 16] = ctot[m][jj][2] + c[m][jj][2];
+      r0[8 * 16 + 1] = ctot[m][jj][3] + c[m][jj][3];
+    }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = tid + 256 * r;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sred[w * 512 + i];
+    a.partials[((size_t)blockIdx.x * 32 + (i >> 4)) * a.Cin + ci0 + (i & 15)] = sum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // ConvTranspose2d(k3, s2) weight gradient (reference models.py:76-78):
 //   dW[ci][co][ky][kx] = sum_{n,iy,ix} xact[n][ci][iy][ix] * dout[n][co][2iy+ky][2ix+kx]
 // = nine skinny GEMMs that share the A operand (xact, M = 16 input channels, K = input pixels) and take their B
@@ -1244,6 +1403,38 @@ int ocrs_det_pw_wgrad_saved(const float* d_a, long long da_ss, const float* y, l
     pw_wgrad_saved_kernel<16><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   }
   OCRS_CHECK_LAUNCH("pw_wgrad_saved_kernel");
+  return 0;
+}
+
+// Rows of the [workers][32][Cin] partials of ocrs_det_pw_wgrad_saved32.
+int ocrs_det_pw_wgrad_saved32_workers(int N, long long HW, int Cin) {
+  const int slices = ocrs_cdiv(Cin, 16);
+  const long long items = (long long)N * ((HW + G32_PX - 1) / G32_PX);
+  long long per = (2 * OCRS_NUM_SMS + slices - 1) / slices;
+  if (per > items) per = items;
+  return (int)(per < 1 ? 1 : per);
+}
+
+// ocrs_det_pw_wgrad_saved for the blocks with exactly 32 output channels (Cin a multiple of 16), always with the fused
+// 1x1 data gradient: partials [workers][32][Cin] fully written, g [N][Cin][HW] view written.
+int ocrs_det_pw_wgrad_saved32(const float* d_a, long long da_ss, const float* y, long long y_ss, int N, long long HW,
+                              const float* sc, const float* sh, const float* lo, const float* k1, const float* k2,
+                              const float* k3, const float* dw_out, int Cin, float* partials, const float* wpw, float* g,
+                              long long g_ss, void* stream) {
+  OCRS_CHECK_ARG(N > 0 && Cin > 0 && Cin % 16 == 0 && HW > 0, "pw_wgrad_saved32: Cin %d must be a multiple of 16", Cin);
+  OCRS_CHECK_ARG(wpw != nullptr && g != nullptr && g_ss % 4 == 0 && (uintptr_t)g % 16 == 0, "pw_wgrad_saved32: needs wpw and a 16-byte aligned g");
+  OCRS_CHECK_ARG(HW % 4 == 0 && da_ss % 4 == 0 && y_ss % 4 == 0 && (uintptr_t)d_a % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+                     (uintptr_t)dw_out % 16 == 0, "pw_wgrad_saved32: planes must be 16-byte aligned (HW %% 4 == 0)");
+  PwWg2Args a;
+  a.d_a = d_a; a.y = y; a.dwo = dw_out; a.da_ss = da_ss; a.y_ss = y_ss;
+  a.sc = sc; a.sh = sh; a.lo = lo; a.k1 = k1; a.k2 = k2; a.k3 = k3; a.partials = partials;
+  a.Cout = 32; a.Cin = Cin; a.N = N; a.HW = HW;
+  a.wpw = wpw; a.g = g; a.g_ss = g_ss;
+  dim3 grid(ocrs_det_pw_wgrad_saved32_workers(N, HW, Cin), Cin / 16);
+  const size_t smem = (size_t)(GSTAGES * G32_STAGE + 16 * G32_PS) * 4;
+  OCRS_SET_SMEM_ONCE(pw_wgrad_saved32_kernel, smem);
+  pw_wgrad_saved32_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  OCRS_CHECK_LAUNCH("pw_wgrad_saved32_kernel");
   return 0;
 }
 

@@ -197,6 +197,15 @@ class _Sep:
         else:
             g = new_view(N, ci, H, W, dev)
             fuse_g = dwo is not None and co <= 16 and FUSE_PWT  # the weight-gradient kernel also emits g (csrc/det_tma.cu)
+            if dwo is not None and co == 32 and ci % 16 == 0 and FUSE_PWT and HW % 4 == 0:
+                # 32 output channels: one CTA holds them all, so g comes out of the same staged tile here too
+                workers = lib.ocrs_det_pw_wgrad_saved32_workers(N, HW, ci)
+                wpart = torch.empty((workers, co, ci), dtype=torch.float32, device=dev)
+                call("ocrs_det_pw_wgrad_saved32", d_a.p, d_a.ss, y.p, y.ss, N, HW, *k, ptr(dwo), ci, ptr(wpart),
+                     ptr(self.pw.weight), g.p, g.ss, st, meta=4.0 * N * HW * (2 * co + 2 * ci))
+                d_wpw = Partial(wpart, workers, co * ci)
+                dwo = None
+                return self._dw_backward(saved, inp, g, dx, d_wpw, coef, N, H, W, st, accumulate, bn_pending)
             if not fuse_g:
                 call("ocrs_det_pwT_bwd", d_a.p, d_a.ss, y.p, y.ss, N, co, HW, *k, ptr(self.pw.weight), ci, g.p, g.ss, st,
                      meta=4.0 * N * HW * (2 * co + ci))
@@ -218,6 +227,14 @@ class _Sep:
                      ptr(self.dw.weight), ptr(wpart), st, meta=4.0 * N * HW * (2 * co + ci))
             d_wpw = Partial(wpart, workers, co * ci)
         dwo = None
+        return self._dw_backward(saved, inp, g, dx, d_wpw, coef, N, H, W, st, accumulate, bn_pending)
+
+    def _dw_backward(self, saved, inp, g, dx, d_wpw, coef, N, H, W, st, accumulate, bn_pending):
+        """Depthwise 3x3 backward of the block from g = d(depthwise output): dx, the depthwise weight gradient and, when this
+        block is the final writer of the upstream block's d_a, that block's BatchNorm-backward sums."""
+        dev = g.t.device
+        lib = _lib.lib()
+        HW, ci = H * W, self.cin
         if dx is None:
             dx = new_view(N, ci, H, W, dev)
         if USE_TMA and lib.ocrs_det_tma_supported(g.p, g.ss, inp.p, inp.ss, H, W) and lib.ocrs_det_tma_supported(dx.p, dx.ss, dx.p, dx.ss, H, W):

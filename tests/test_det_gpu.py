@@ -163,6 +163,42 @@ def test_pw_wgrad_from_saved_depthwise_output(N, cin, cout, HW):
         assert rel_l2(gout, torch.einsum("oi,nop->nip", wpw.double(), dy)) < 2e-6
 
 
+@pytest.mark.parametrize("N,cin,HW", [(2, 32, 64 * 48), (1, 16, 1000), (3, 64, 132), (1, 32, 64), (2, 32, 8)])
+def test_pw_wgrad_saved_32_output_channels_with_data_gradient(N, cin, HW):
+    """ocrs_det_pw_wgrad_saved32: the blocks with 32 output channels; weight gradient partials and the fused 1x1 data
+    gradient from one staged tile (what ocrs_det_pw_wgrad_saved + ocrs_det_pwT_bwd compute in two passes)."""
+    from ocrs_models_b200 import _lib
+    from ocrs_models_b200._lib import call, ptr
+
+    lib = _lib.lib()
+    cout = 32
+    g = torch.Generator().manual_seed(cin * 7 + HW)
+    dwo = torch.randn(N, cin, HW, generator=g)
+    y = torch.randn(N, cout, HW, generator=g)
+    d_a = torch.randn(N, cout, HW, generator=g)
+    yxf = _rand_xf(cout, g)
+    k1, k2, k3 = (torch.randn(cout, generator=g) for _ in range(3))
+    wpw = torch.randn(cout, cin, generator=g)
+    act = (y.double() * yxf[0][None, :, None] + yxf[1][None, :, None]) > 0
+    dy = k1[None, :, None] * (d_a.double() * act) + k2[None, :, None] * y.double() + k3[None, :, None]
+    workers = lib.ocrs_det_pw_wgrad_saved32_workers(N, HW, cin)
+    part = torch.full((workers, cout, cin), float("nan"), device="cuda")
+    # d_a and y as channel slices of wider buffers (sample stride > 32 planes), g into a slice too
+    da_buf = torch.zeros(N, cout + 4, HW, device="cuda")
+    da_buf[:, :cout] = d_a.cuda()
+    y_buf = torch.zeros(N, cout + 8, HW, device="cuda")
+    y_buf[:, :cout] = y.cuda()
+    g_buf = torch.full((N, cin + 4, HW), float("nan"), device="cuda")
+    dev = [t.cuda() for t in (*yxf, k1, k2, k3, dwo, wpw)]
+    call("ocrs_det_pw_wgrad_saved32", ptr(da_buf), (cout + 4) * HW, ptr(y_buf), (cout + 8) * HW, N, HW, ptr(dev[0]), ptr(dev[1]),
+         ptr(dev[2]), ptr(dev[3]), ptr(dev[4]), ptr(dev[5]), ptr(dev[6]), cin, ptr(part), ptr(dev[7]), ptr(g_buf), (cin + 4) * HW,
+         _stream())
+    torch.cuda.synchronize()
+    assert rel_l2(part.double().sum(0), torch.einsum("nop,nip->oi", dy, dwo.double())) < 2e-5
+    assert rel_l2(g_buf[:, :cin], torch.einsum("oi,nop->nip", wpw.double(), dy)) < 2e-6
+    assert torch.isnan(g_buf[:, cin:]).all()
+
+
 @pytest.mark.parametrize("N,C,H,W,acc", [(2, 8, 40, 36, True), (1, 5, 70, 132, False), (2, 16, 32, 64, True), (1, 1, 9, 8, False)])
 def test_tma_dw_bwd_with_fused_upstream_bn_reduction(N, C, H, W, acc):
     """ocrs_det_sep_dw_bwd: dx (accumulated into a strided channel slice), dw weight gradient, and the BatchNorm-backward
