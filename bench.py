@@ -158,7 +158,15 @@ class Workload:
     def step_e2e(self):
         """Public-API step from HOST buffers: H2D of the inputs, the step, D2H of the loss."""
         if self.graphed is not None:
-            return float(self.graphed({k: self.host[k] for k in ("image", "mask", "targets") if k in self.host}).item())
+            # pipelined like an input loader with prefetch: the H2D copy of the NEXT step's inputs is issued on a copy
+            # stream right after this step's replay is launched; every step still consumes one freshly copied host batch
+            hb = {k: self.host[k] for k in ("image", "mask", "targets") if k in self.host}
+            g = self.graphed
+            if not g._has_staged:
+                g.prefetch(hb)
+            loss = g()
+            g.prefetch(hb)
+            return float(loss.item())
         b = dict(self.host)
         for k in ("image", "mask", "targets"):
             if k in b:
@@ -503,7 +511,10 @@ def measure(kind, args, device, rank, world, dist_on, pk):
     res = {
         "value": units * args.steps / (ms * 1e-3), "unit": unit, "ms_per_step": ms / args.steps,
         "e2e": {"value": units * args.steps / (wall * 1e-3), "unit": unit, "h2d_bytes_per_step": wl.h2d_bytes,
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4,
+                # with the graphed step the H2D copy of step i+1's host batch runs on a copy stream during step i (one copy per
+                # step, all inside the timed region), like a data loader with prefetch; the loss read-back syncs every step
+                "input_prefetch": bool(graph_on)},
         "gpu_launches": int(launches), "clocks": cs.summary(), "first_step_loss": check,
         "cuda_graph": bool(graph_on) if graph_on else {"enabled": False, "why": getattr(wl, "graph_error", "--no-graph")},
     }

@@ -164,11 +164,45 @@ class GraphedTrainStep:
             if isinstance(v, torch.Tensor):
                 self.static[k].copy_(v, non_blocking=True)
 
+    # ---- input prefetch: the host->device copy of the NEXT batch runs on its own stream while the current step replays ----
+    _copy_stream = None
+    _has_staged = False
+
+    def prefetch(self, batch: dict):
+        """Start copying `batch` (pinned host tensors) into device staging buffers on a copy stream. The next `step()`
+        call without a batch waits for it, moves it into the graph's static buffers (device-to-device) and replays."""
+        dev = self.opt.dev
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items() if isinstance(v, torch.Tensor)}
+            self._staged_ev = torch.cuda.Event()
+            self._free_ev = torch.cuda.Event()
+            self._free_ev.record(torch.cuda.current_stream(dev))
+        cs = self._copy_stream
+        cs.wait_event(self._free_ev)  # the previous batch has left the staging buffers
+        with torch.cuda.stream(cs):
+            for k, v in batch.items():
+                if isinstance(v, torch.Tensor):
+                    self._staging[k].copy_(v, non_blocking=True)
+            self._staged_ev.record(cs)
+        self._staged_keys = [k for k, v in batch.items() if isinstance(v, torch.Tensor)]
+        self._has_staged = True
+
+    def _consume_staged(self):
+        main = torch.cuda.current_stream(self.opt.dev)
+        main.wait_event(self._staged_ev)
+        for k in self._staged_keys:
+            self.static[k].copy_(self._staging[k], non_blocking=True)
+        self._free_ev.record(main)
+        self._has_staged = False
+
     def __call__(self, batch: dict | None = None) -> torch.Tensor:
         """Replay the step (after copying `batch` into the static buffers when given). Returns the device loss tensor of
         this step (overwritten by the next replay)."""
         if batch is not None:
             self.load(batch)
+        elif self._has_staged:
+            self._consume_staged()
         self.graph.replay()
         if self.split:
             self.opt._synced = False

@@ -55,3 +55,39 @@ def test_graphed_step_equals_eager_step(kind):
     assert l0 == l1, (l0, l1)
     for k in s0:
         assert torch.equal(s0[k], s1[k]), k
+
+
+def test_prefetched_batches_give_the_same_steps():
+    """GraphedTrainStep.prefetch: batches copied on the copy stream one step ahead must produce exactly the steps that
+    `step(batch)` produces (same losses, same weights)."""
+    from ocrs_models_b200 import DetectionModel, balanced_cross_entropy_loss
+    from ocrs_models_b200.optim import FusedAdam, GraphedTrainStep
+
+    g = torch.Generator().manual_seed(3)
+    batches = [{"image": (torch.rand(2, 1, 64, 64, generator=g) - 0.5).pin_memory(), "mask": (torch.rand(2, 1, 64, 64, generator=g) < 0.1).float().pin_memory()}
+               for _ in range(5)]
+    loss_of = lambda m, b: balanced_cross_entropy_loss(m(b["image"]), b["mask"])  # noqa: E731
+    out = []
+    for prefetch in (False, True):
+        torch.manual_seed(1234)
+        model = DetectionModel().cuda().train()
+        opt = FusedAdam(model, lr=1e-3)
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        step = GraphedTrainStep(model, opt, loss_of, batches[0], warmup=2)
+        model.load_state_dict(sd0)
+        opt.m.zero_(); opt.v.zero_(); opt.step_dev.zero_(); opt.t = 0
+        losses = []
+        if prefetch:
+            step.prefetch(batches[0])
+            for i in range(len(batches)):
+                loss = step()
+                if i + 1 < len(batches):
+                    step.prefetch(batches[i + 1])  # overlaps the replay just launched
+                losses.append(float(loss.item()))
+        else:
+            for b in batches:
+                losses.append(float(step(b).item()))
+        out.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    assert out[0][0] == out[1][0]
+    for k in out[0][1]:
+        assert torch.equal(out[0][1][k], out[1][1][k]), k
