@@ -1,10 +1,10 @@
 // Recognition (CRNN) kernels that are not plain GEMMs (reference ocrs_models/models.py:179-268).
 //
 // Activations of the conv stack are NHWC fp32. conv.0 (Cin = 1) is a direct convolution fused
-// with ReLU + MaxPool2 (models.py:180-187); every other convolution is im2col + GEMM (gemm.cu)
+// with ReLU + MaxPool2 (models.py:180-187); every other convolution is an implicit GEMM on tcgen05 (gemm_tc.cu; conv.19, 2x2: im2col + GEMM)
 // followed by one fused BatchNorm-affine / ReLU / pool kernel here. The GRU recurrence
-// (models.py:245, gate equations torch/nn/modules/rnn.py) runs one launch per time step for both
-// directions; LogSoftmax (models.py:250) is one warp per row.
+// (models.py:245) lives in gru_persist.cu (one cluster-persistent launch per layer); LogSoftmax
+// (models.py:250) is one warp per row.
 #include "common.cuh"
 #include <math.h>
 

@@ -1,4 +1,7 @@
-"""Execution plan of the detection U-Net on the sm_100a kernels (csrc/det_fwd.cu, det_bwd.cu).
+"""Execution plan of the detection U-Net on the sm_100a kernels (csrc/det_tma.cu: TMA / cp.async-pipelined blocks of the
+8-32 channel levels; csrc/gemm_tc.cu: batched tcgen05 GEMMs of the >= 64 channel levels; csrc/det_convt.cu: ConvTranspose2d
+tile kernels; csrc/det_fwd.cu, det_bwd.cu: pooling, out_conv, BatchNorm finalisation and the kernels for shapes TMA cannot
+address).
 
 Follows reference ``DetectionModel.forward`` (ocrs_models/models.py:131-143) op for op, but:
 
@@ -6,7 +9,8 @@ Follows reference ``DetectionModel.forward`` (ocrs_models/models.py:131-143) op 
   ``torch.cat`` of ``Up.forward`` (models.py:89) is two producers writing into one buffer;
 * BatchNorm+ReLU of a block is folded into the loads of its consumers (per-channel scale/shift/lo);
 * the whole forward is one ``torch.autograd.Function`` whose backward runs the hand-written
-  backward kernels and returns every parameter gradient.
+  backward kernels; parameter gradients leave them as partial rows and are reduced and delivered (returned to autograd,
+  or accumulated into an attached ``optim.FusedAdam`` bucket) by one multi-tensor launch (``grads.deliver``).
 """
 from __future__ import annotations
 
