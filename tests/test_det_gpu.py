@@ -427,7 +427,7 @@ def _det_models(seed=1234):
     return m
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 96, 80), (1, 200, 152), (2, 64, 64)])
+@pytest.mark.parametrize("N,H,W", [(2, 96, 80), (1, 200, 152), (2, 64, 64), (1, 256, 320)])
 def test_full_model_train_step_vs_oracle(N, H, W):
     from ocrs_models_b200 import balanced_cross_entropy_loss
 
