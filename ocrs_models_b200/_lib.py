@@ -95,9 +95,9 @@ SIGNATURES: dict[str, list] = {
     "ocrs_colsum_rows": [I],
     "ocrs_colsum": [P, L, I, I, P, P],
     # recognition (csrc/rec.cu)
-    "ocrs_rec_conv0_fwd": [P, I, I, I, P, P, P, P],
+    "ocrs_rec_conv0_fwd": [P, I, I, I, P, P, P, P, P],
     "ocrs_rec_conv0_bwd_blocks": [],
-    "ocrs_rec_conv0_bwd": [P, I, I, I, P, P, P, P, P],
+    "ocrs_rec_conv0_bwd": [P, I, I, I, P, P, P, P, P, P],
     "ocrs_rec_bn_act_pool_fwd": [P, I, I, I, I, I, I, I, I, P, P, P, L, L, L, P],
     "ocrs_rec_pool_bwd_blocks": [],
     "ocrs_rec_bn_act_pool_bwd_reduce": [P, I, I, I, I, I, I, I, I, P, P, P, P, P, L, L, L, P, P],

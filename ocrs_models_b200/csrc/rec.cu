@@ -25,7 +25,7 @@ __device__ __forceinline__ void conv0_patch(const float* __restrict__ x, int H, 
 
 __global__ void __launch_bounds__(256)
 conv0_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
-                 const float* __restrict__ bias, float* __restrict__ out) {
+                 const float* __restrict__ bias, float* __restrict__ out, unsigned* __restrict__ code) {
   __shared__ __align__(16) float sw[9 * 32];
   __shared__ float sb[32];
   for (int i = threadIdx.x; i < 288; i += 256) sw[(i % 9) * 32 + i / 9] = w[i];  // [tap][c]
@@ -43,6 +43,7 @@ conv0_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* 
   float p[4][4];
   conv0_patch(x, H, W, n, py, px, p);
   float best[8];
+  unsigned arg = 0;  // 2 bits per channel: window position of the FIRST maximum (aten's tie rule), for the backward pass
 #pragma unroll
   for (int c = 0; c < 8; ++c) best[c] = -INFINITY;
 #pragma unroll
@@ -58,7 +59,16 @@ conv0_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* 
       for (int c = 0; c < 8; ++c) v[c] = fmaf(xv, sw[k * 32 + cg * 8 + c], v[c]);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], v[c]);
+    for (int c = 0; c < 8; ++c) {
+      if (q == 0) best[c] = v[c];
+      else if (v[c] > best[c]) { best[c] = v[c]; arg = (arg & ~(3u << (2 * c))) | ((unsigned)q << (2 * c)); }
+    }
+  }
+  if (code) {  // bits 0-15: arg-max positions, bits 16-23: pre-activation maximum > 0 (the ReLU gate)
+    unsigned pos = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pos |= (best[c] > 0.f ? 1u : 0u) << c;
+    code[i] = arg | (pos << 16);
   }
   float4* o = reinterpret_cast<float4*>(out + ((((size_t)n * Hp + py) * Wp + px) * 32 + cg * 8));
   o[0] = make_float4(fmaxf(best[0], 0.f), fmaxf(best[1], 0.f), fmaxf(best[2], 0.f), fmaxf(best[3], 0.f));
@@ -70,7 +80,7 @@ conv0_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* 
 // partials: [gridDim.x][32][10] (9 taps + bias).
 __global__ void __launch_bounds__(256)
 conv0_bwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
-                 const float* __restrict__ bias, const float* __restrict__ dout,
+                 const float* __restrict__ bias, const float* __restrict__ dout, const unsigned* __restrict__ code,
                  float* __restrict__ partials) {
   __shared__ __align__(16) float sw[9 * 32];
   __shared__ float sb[32];
@@ -96,27 +106,37 @@ conv0_bwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* 
     const float4* gp = reinterpret_cast<const float4*>(dout + ((((size_t)n * Hp + py) * Wp + px) * 32 + cg * 8));
     const float4 g0 = gp[0], g1 = gp[1];
     const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    float v[4][8];
+    unsigned cw = 0;
+    if (code) {
+      cw = code[i];  // arg-max positions and ReLU gates saved by the forward pass: no recompute of the 4 x 9 x 8 products
+    } else {
+      float v[4][8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int dy = q >> 1, dx = q & 1;
+      for (int q = 0; q < 4; ++q) {
+        const int dy = q >> 1, dx = q & 1;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v[q][c] = sb[cg * 8 + c];
+        for (int c = 0; c < 8; ++c) v[q][c] = sb[cg * 8 + c];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float xv = p[dy + k / 3][dx + k % 3];
+        for (int k = 0; k < 9; ++k) {
+          const float xv = p[dy + k / 3][dx + k % 3];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[q][c] = fmaf(xv, sw[k * 32 + cg * 8 + c], v[q][c]);
+          for (int c = 0; c < 8; ++c) v[q][c] = fmaf(xv, sw[k * 32 + cg * 8 + c], v[q][c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        unsigned am = 0;
+        float m = v[0][c];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (v[q][c] > m) { m = v[q][c]; am = q; }
+        cw |= (am << (2 * c)) | ((m > 0.f ? 1u : 0u) << (16 + c));
       }
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      int am = 0;
-      float m = v[0][c];
-#pragma unroll
-      for (int q = 1; q < 4; ++q)
-        if (v[q][c] > m) { m = v[q][c]; am = q; }
-      const float gv = m > 0.f ? g[c] : 0.f;
+      const int am = (cw >> (2 * c)) & 3;
+      const float gv = ((cw >> (16 + c)) & 1u) ? g[c] : 0.f;
       acc[c][9] += gv;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -525,20 +545,23 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 
 extern "C" {
 
+// conv.0 + ReLU + MaxPool2d(2) -> NHWC [N][H/2][W/2][32]. code (optional, [N * H/2 * W/2 * 4] int32 words): per pooled pixel and
+// 8-channel group the arg-max window positions and ReLU gates, which ocrs_rec_conv0_bwd then uses instead of recomputing.
 int ocrs_rec_conv0_fwd(const float* x, int N, int H, int W, const float* w, const float* bias, float* out,
-                       void* stream) {
+                       int* code, void* stream) {
   OCRS_CHECK_ARG(H >= 2 && W >= 2, "conv0_fwd: input too small");
   const long long total = (long long)N * (H / 2) * (W / 2) * 4;
-  conv0_fwd_kernel<<<ocrs_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, w, bias, out);
+  conv0_fwd_kernel<<<ocrs_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, w, bias, out, reinterpret_cast<unsigned*>(code));
   OCRS_CHECK_LAUNCH("conv0_fwd_kernel");
   return 0;
 }
 
 int ocrs_rec_conv0_bwd_blocks(void) { return 4 * OCRS_NUM_SMS; }
-// partials: [blocks][32][10]
+// Weight / bias gradient of conv.0 (its input is the image: no data gradient). partials: [blocks][32][10] (9 taps + bias).
+// code: what ocrs_rec_conv0_fwd saved, or null to recompute the pre-pool values here.
 int ocrs_rec_conv0_bwd(const float* x, int N, int H, int W, const float* w, const float* bias,
-                       const float* dout, float* partials, void* stream) {
-  conv0_bwd_kernel<<<ocrs_rec_conv0_bwd_blocks(), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, w, bias, dout, partials);
+                       const float* dout, const int* code, float* partials, void* stream) {
+  conv0_bwd_kernel<<<ocrs_rec_conv0_bwd_blocks(), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, w, bias, dout, reinterpret_cast<const unsigned*>(code), partials);
   OCRS_CHECK_LAUNCH("conv0_bwd_kernel");
   return 0;
 }

@@ -283,7 +283,9 @@ class _RecFunction(torch.autograd.Function):
             # conv.0 + ReLU + MaxPool2 -> NHWC [N, H/2, W/2, 32]
             H1, W1 = H // 2, W // 2
             a0 = _empty((N, H1, W1, 32), dev)
-            call("ocrs_rec_conv0_fwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(a0), st)
+            # training: keep the arg-max positions / ReLU gates (4 bytes per pooled pixel and 8 channels) for conv.0's backward
+            code0 = torch.empty((N * H1 * W1 * 4,), dtype=torch.int32, device=dev) if save else None
+            call("ocrs_rec_conv0_fwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(a0), ptr(code0), st)
 
             def conv_bn_pool(inp, Hh, Ww, cin, conv, bn, ph, pw, mode, relu, kh=3, pad=1, out_strides=None, out=None):
                 cout = conv.out_channels
@@ -360,7 +362,7 @@ class _RecFunction(torch.autograd.Function):
             ctx.model = model
             ctx.rec = rec
             ctx.gru_rec = gru_rec
-            ctx.misc = (x, a0, lp, N, H, W, T, C, bool(training))
+            ctx.misc = (x, code0, lp, N, H, W, T, C, bool(training))
             ctx.wprep = wprep
         return lp
 
@@ -368,7 +370,7 @@ class _RecFunction(torch.autograd.Function):
     def backward(ctx, g_lp):
         model = ctx.model
         rec, gru_rec = ctx.rec, ctx.gru_rec
-        x, a0, lp, N, H, W, T, C, training = ctx.misc
+        x, code0, lp, N, H, W, T, C, training = ctx.misc
         wdg, wsplit, whhT_of = ctx.wprep["dg"], ctx.wprep["w"], ctx.wprep["whhT"]
         dev = lp.device
         st = _lib.stream_ptr(dev)
@@ -482,7 +484,7 @@ class _RecFunction(torch.autograd.Function):
             d_a0 = stage("3", None, d_a3, "4")
             blocks = lib.ocrs_rec_conv0_bwd_blocks()
             part = _empty((blocks, 32, 10), dev)
-            call("ocrs_rec_conv0_bwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(d_a0), ptr(part), st)
+            call("ocrs_rec_conv0_bwd", ptr(x), N, H, W, ptr(cv["0"].weight), ptr(cv["0"].bias), ptr(d_a0), ptr(code0), ptr(part), st)
             grads[id(cv["0"].weight)] = Partial(part, blocks, 288, ld=320, inner=(9, 10))
             grads[id(cv["0"].bias)] = Partial(part, blocks, 32, ld=320, off=9, inner=(1, 10))
             param_grads = deliver(list(model.parameters()), grads, st)

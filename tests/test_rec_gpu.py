@@ -146,15 +146,22 @@ def test_conv0_fwd_bwd():
     ref.backward(dout.double())
     xd, wd, bd = x.cuda(), w.detach().float().cuda(), b.detach().float().cuda()
     out = torch.empty(N, H // 2, W // 2, 32, device="cuda")
-    call("ocrs_rec_conv0_fwd", ptr(xd), N, H, W, ptr(wd), ptr(bd), ptr(out), _st())
+    code = torch.empty(N * (H // 2) * (W // 2) * 4, dtype=torch.int32, device="cuda")
+    call("ocrs_rec_conv0_fwd", ptr(xd), N, H, W, ptr(wd), ptr(bd), ptr(out), ptr(code), _st())
     assert rel_l2(out.permute(0, 3, 1, 2), ref) < 1e-5
+    out2 = torch.empty_like(out)
+    call("ocrs_rec_conv0_fwd", ptr(xd), N, H, W, ptr(wd), ptr(bd), ptr(out2), None, _st())  # inference: no code
+    assert torch.equal(out, out2)
     blocks = lib().ocrs_rec_conv0_bwd_blocks()
     part = torch.empty(blocks, 32, 10, device="cuda")
     dd = dout.permute(0, 2, 3, 1).contiguous().cuda()
-    call("ocrs_rec_conv0_bwd", ptr(xd), N, H, W, ptr(wd), ptr(bd), ptr(dd), ptr(part), _st())
+    call("ocrs_rec_conv0_bwd", ptr(xd), N, H, W, ptr(wd), ptr(bd), ptr(dd), None, ptr(part), _st())  # recomputing path
     got = part.sum(0)
     assert rel_l2(got[:, :9].reshape(32, 1, 3, 3), w.grad) < 1e-4
     assert rel_l2(got[:, 9], b.grad) < 1e-4
+    part2 = torch.empty_like(part)
+    call("ocrs_rec_conv0_bwd", ptr(xd), N, H, W, ptr(wd), ptr(bd), ptr(dd), ptr(code), ptr(part2), _st())  # saved arg-max / gates
+    assert torch.equal(part, part2)
 
 
 @pytest.mark.parametrize("T,N", [(9, 3), (25, 64), (6, 70)])
