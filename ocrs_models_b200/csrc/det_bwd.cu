@@ -117,11 +117,32 @@ bnrelu_bwd_reduce_kernel(const float* __restrict__ d_a, long long da_ss,
   const long long i0 = (long long)blockIdx.x * RED_CHUNK;
   const long long i1 = min(i0 + RED_CHUNK, HW);
   float a = 0.f, b = 0.f;
-  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
-    const float yv = yp[i];
-    const float dz = (fmaf(yv, s, t) > l) ? dp[i] : 0.f;
-    a += dz;
-    b = fmaf(dz, (yv - mu) * is, b);
+  if (i0 + RED_CHUNK <= HW && (((uintptr_t)(dp + i0) | (uintptr_t)(yp + i0)) & 15) == 0) {
+    // full, 16-byte aligned chunk: 4 + 4 independent 16-byte loads per thread in flight (the scalar loop ran at 2.4 TB/s)
+    float4 yv[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + 4 * (threadIdx.x + 256 * u);
+      yv[u] = *reinterpret_cast<const float4*>(yp + i);
+      dv[u] = *reinterpret_cast<const float4*>(dp + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float ys[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w}, ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float dz = (fmaf(ys[q], s, t) > l) ? ds[q] : 0.f;
+        a += dz;
+        b = fmaf(dz, (ys[q] - mu) * is, b);
+      }
+    }
+  } else {
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+      const float yv = yp[i];
+      const float dz = (fmaf(yv, s, t) > l) ? dp[i] : 0.f;
+      a += dz;
+      b = fmaf(dz, (yv - mu) * is, b);
+    }
   }
   a = block_sum(a, red);
   b = block_sum(b, red);
@@ -177,12 +198,21 @@ __device__ __forceinline__ float dy_of(float da, float yv, float s, float t, flo
 __global__ void __launch_bounds__(256)
 dy_kernel(const float* __restrict__ d_a, long long da_ss, const float* __restrict__ y, long long y_ss, int C,
           long long HW, DyCoef k, float* __restrict__ dy) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;  // four consecutive pixels per thread
   const int c = blockIdx.y, n = blockIdx.z;
   if (i >= HW) return;
   const size_t off = (size_t)c * HW + i;
-  dy[((size_t)n * C + c) * HW + i] = dy_of(d_a[(size_t)n * da_ss + off], y[(size_t)n * y_ss + off], k.sc[c], k.sh[c],
-                                           k.lo[c], k.k1[c], k.k2[c], k.k3[c]);
+  const float* dp = d_a + (size_t)n * da_ss + off;
+  const float* yp = y + (size_t)n * y_ss + off;
+  float* op = dy + ((size_t)n * C + c) * HW + i;
+  const float sc = k.sc[c], sh = k.sh[c], lo = k.lo[c], k1 = k.k1[c], k2 = k.k2[c], k3 = k.k3[c];
+  if (i + 4 <= HW && (((uintptr_t)dp | (uintptr_t)yp | (uintptr_t)op) & 15) == 0) {
+    const float4 d = *reinterpret_cast<const float4*>(dp), v = *reinterpret_cast<const float4*>(yp);
+    *reinterpret_cast<float4*>(op) = make_float4(dy_of(d.x, v.x, sc, sh, lo, k1, k2, k3), dy_of(d.y, v.y, sc, sh, lo, k1, k2, k3),
+                                                 dy_of(d.z, v.z, sc, sh, lo, k1, k2, k3), dy_of(d.w, v.w, sc, sh, lo, k1, k2, k3));
+  } else {
+    for (int q = 0; q < 4 && i + q < HW; ++q) op[q] = dy_of(dp[q], yp[q], sc, sh, lo, k1, k2, k3);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -957,7 +987,7 @@ int ocrs_det_dy(const float* d_a, long long da_ss, const float* y, long long y_s
                 const float* sc, const float* sh, const float* lo, const float* k1, const float* k2, const float* k3,
                 float* dy, void* stream) {
   DyCoef k{sc, sh, lo, k1, k2, k3};
-  dim3 grid(ocrs_cdiv(HW, 256), Cout, N);
+  dim3 grid(ocrs_cdiv(HW, 1024), Cout, N);
   dy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, da_ss, y, y_ss, Cout, HW, k, dy);
   OCRS_CHECK_LAUNCH("dy_kernel");
   return 0;

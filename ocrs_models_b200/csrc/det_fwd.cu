@@ -408,25 +408,30 @@ activate_kernel(const float* __restrict__ x, long long x_ss, int C, long long HW
 __global__ void __launch_bounds__(256)
 convt_col2im_kernel(const float* __restrict__ Z /*[N][Cout*9][Hin*Win]*/, int Cout, int Hin, int Win,
                     const float* __restrict__ bias, float* __restrict__ out, long long out_ss, int Hs, int Ws) {
-  const int ox = blockIdx.x * 32 + threadIdx.x, oy = blockIdx.y * 8 + threadIdx.y;
+  // thread = input position (qy, qx) = the 2x2 output quad (2qy.., 2qx..): nine row-contiguous reads of Z, two 8-byte stores.
+  // qy == Hin / qx == Win (odd crops) only receive the ky == 2 / kx == 2 taps of the last input row / column.
+  const int qx = blockIdx.x * 32 + threadIdx.x, qy = blockIdx.y * 8 + threadIdx.y;
   const int co = blockIdx.z % Cout, n = blockIdx.z / Cout;
+  const int oy = 2 * qy, ox = 2 * qx;
   if (ox >= Ws || oy >= Hs) return;
   const size_t HWi = (size_t)Hin * Win;
   const float* zc = Z + ((size_t)n * Cout + co) * 9 * HWi;
-  // rows: oy even -> ky = 0 from qy = oy/2 and ky = 2 from qy = oy/2 - 1; oy odd -> ky = 1 from qy = (oy-1)/2. Same for columns.
-  const int qy0 = oy >> 1, qx0 = ox >> 1;
-  const int nky = (oy & 1) ? 1 : 2, nkx = (ox & 1) ? 1 : 2;
-  float acc = bias ? bias[co] : 0.f;
-  for (int a = 0; a < nky; ++a) {
-    const int ky = (oy & 1) ? 1 : 2 * a, qy = qy0 - a;
-    if (qy < 0 || qy >= Hin) continue;
-    for (int b = 0; b < nkx; ++b) {
-      const int kx = (ox & 1) ? 1 : 2 * b, qx = qx0 - b;
-      if (qx < 0 || qx >= Win) continue;
-      acc += zc[(size_t)(ky * 3 + kx) * HWi + (size_t)qy * Win + qx];
-    }
+  const bool y0 = qy < Hin, y1 = qy >= 1, x0 = qx < Win, x1 = qx >= 1;  // (qy, qx), (qy-1, .), (., qx-1) inside the input
+  const size_t p = (size_t)qy * Win + qx;
+  auto z = [&](int k, bool ok, size_t at) { return ok ? zc[(size_t)k * HWi + at] : 0.f; };
+  const float b = bias ? bias[co] : 0.f;
+  const float o00 = b + z(0, y0 && x0, p) + z(6, y1 && x0, p - Win) + z(2, y0 && x1, p - 1) + z(8, y1 && x1, p - Win - 1);
+  const float o01 = b + z(1, y0 && x0, p) + z(7, y1 && x0, p - Win);
+  const float o10 = b + z(3, y0 && x0, p) + z(5, y0 && x1, p - 1);
+  const float o11 = b + z(4, y0 && x0, p);
+  float* o = out + (size_t)n * out_ss + (size_t)co * Hs * Ws + (size_t)oy * Ws + ox;
+  const bool pair = ox + 1 < Ws, vec = pair && ((reinterpret_cast<uintptr_t>(o) & 7) == 0) && (Ws % 2 == 0);
+  if (vec) *reinterpret_cast<float2*>(o) = make_float2(o00, o01);
+  else { o[0] = o00; if (pair) o[1] = o01; }
+  if (oy + 1 < Hs) {
+    if (vec) *reinterpret_cast<float2*>(o + Ws) = make_float2(o10, o11);
+    else { o[Ws] = o10; if (pair) o[Ws + 1] = o11; }
   }
-  out[(size_t)n * out_ss + (size_t)co * Hs * Ws + (size_t)oy * Ws + ox] = acc;
 }
 
 }  // namespace
@@ -455,7 +460,7 @@ int ocrs_det_convt_col2im(const float* Z, int N, int Cout, int Hin, int Win, con
   OCRS_CHECK_ARG(N > 0 && Cout > 0 && Hin > 0 && Win > 0, "convt_col2im: bad dims");
   OCRS_CHECK_ARG(Hs <= 2 * Hin + 1 && Ws <= 2 * Win + 1, "convt_col2im: crop %dx%d exceeds %dx%d", Hs, Ws, 2 * Hin + 1,
                  2 * Win + 1);
-  dim3 block(32, 8), grid(ocrs_cdiv(Ws, 32), ocrs_cdiv(Hs, 8), N * Cout);
+  dim3 block(32, 8), grid(ocrs_cdiv((Ws + 1) / 2, 32), ocrs_cdiv((Hs + 1) / 2, 8), N * Cout);
   convt_col2im_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Z, Cout, Hin, Win, bias, out, out_ss, Hs, Ws);
   OCRS_CHECK_LAUNCH("convt_col2im_kernel");
   return 0;
